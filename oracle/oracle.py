@@ -1,0 +1,363 @@
+"""CPU oracle for the SfmFromScratch feature hot path (numpy half).
+
+TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import this
+module; the product package ``sfmfromscratch_b200`` never does and has no CPU
+fallback.
+
+This is a restatement, not a copy, of the reference's algorithm.  The dense
+per-pixel arithmetic lives in ``oracle/sfm_oracle.c`` (explicit ``fmaf``
+chains, which numpy cannot express); this file holds the selection logic and
+the histogram descriptors, calling the same numpy primitives the reference
+calls where their bit-level behaviour matters (``np.median``, ``np.histogram``,
+``np.arctan2``, ``np.linalg.norm``).  The reference's O(H*W) Python NMS loop is
+replaced by the C window maximum, which is what makes full-size parity runs
+finish in seconds.
+
+Parity status: the reference has no tests or golden vectors, so the oracle is
+pinned against the reference itself executed in the build container:
+``tests/golden/make_golden.py`` imports ``/root/reference`` and writes the
+fixtures under ``tests/golden/``; ``tests/test_oracle_vs_golden.py`` checks this
+file against them everywhere, ``tests/test_oracle_vs_reference.py`` against the
+live reference when ``/root/reference`` exists.
+
+Reference citations are relative to the reference root.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from typing import Optional, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "sfm_oracle.c")
+_LIB = os.path.join(_HERE, "_build", "libsfm_oracle.so")
+_fp = ctypes.POINTER(ctypes.c_float)
+_i64p = ctypes.POINTER(ctypes.c_int64)
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile sfm_oracle.c with gcc into oracle/_build/ (idempotent)."""
+    if (not force and os.path.exists(_LIB)
+            and os.path.getmtime(_LIB) >= os.path.getmtime(_SRC)):
+        return _LIB
+    os.makedirs(os.path.dirname(_LIB), exist_ok=True)
+    cmd = ["gcc", "-O2", "-mfma", "-ffp-contract=off", "-fPIC", "-shared",
+           "-fvisibility=hidden", "-o", _LIB, _SRC, "-lm"]
+    subprocess.run(cmd, check=True)
+    return _LIB
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(build())
+        c_int, c_float = ctypes.c_int, ctypes.c_float
+        L.orc_sobel.argtypes = [_fp, c_int, c_int, _fp, _fp]
+        L.orc_filter2d.argtypes = [_fp, c_int, c_int, _fp, c_int, _fp]
+        L.orc_harris_response.argtypes = [_fp, c_int, c_int, _fp, c_int, c_float, _fp]
+        L.orc_harris_response.restype = c_int
+        L.orc_maxpool.argtypes = [_fp, c_int, c_int, c_int, _fp]
+        L.orc_resize_half.argtypes = [_fp, c_int, c_int, _fp]
+        L.orc_resize_bilinear.argtypes = [_fp, c_int, c_int, _fp, c_int, c_int]
+        L.orc_dist.argtypes = [_fp, _fp, c_int]
+        L.orc_dist.restype = c_float
+        L.orc_match_top2.argtypes = [_fp, c_int, c_int, _fp, c_int, c_int, _i64p, _fp, _fp]
+        L.orc_dist_matrix.argtypes = [_fp, c_int, _fp, c_int, c_int, _fp]
+        _lib = L
+    return _lib
+
+
+def _f32c(a: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _p(a: np.ndarray):
+    return a.ctypes.data_as(_fp)
+
+
+# --------------------------------------------------------------------------
+# dense per-pixel stages (C)
+# --------------------------------------------------------------------------
+
+def gaussian_kernel(ksize: int, sigma: float) -> np.ndarray:
+    """NaiveSIFT.py:175-199 (_generate_gaussian_kernel): float64 ksize x ksize."""
+    mean = ksize // 2
+    axis = np.linspace(-mean, mean, ksize)
+    x_square = axis[:, np.newaxis] ** 2
+    y_square = axis[np.newaxis, :] ** 2
+    kernel = (1 / (2 * np.pi * sigma ** 2)) * np.exp(-(x_square + y_square) / (2 * sigma ** 2))
+    return kernel / np.sum(kernel)
+
+
+def image_gradients(img: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """NaiveSIFT.py:201-213 (_compute_image_gradients)."""
+    img = _f32c(img)
+    H, W = img.shape
+    Ix = np.empty_like(img)
+    Iy = np.empty_like(img)
+    lib().orc_sobel(_p(img), H, W, _p(Ix), _p(Iy))
+    return Ix, Iy
+
+
+def harris_response(img: np.ndarray, gaussian_size: int = 7, sigma: float = 5,
+                    alpha: float = 0.05) -> np.ndarray:
+    """NaiveSIFT.py:60-74: R map, float32, bit-exact with the reference."""
+    img = _f32c(img)
+    H, W = img.shape
+    gk = _f32c(gaussian_kernel(gaussian_size, sigma))  # cv2 casts the kernel to f32
+    R = np.empty_like(img)
+    rc = lib().orc_harris_response(_p(img), H, W, _p(gk), gaussian_size, np.float32(alpha), _p(R))
+    if rc != 0:
+        raise MemoryError("orc_harris_response")
+    return R
+
+
+def maxpool(R: np.ndarray, ksize: int) -> np.ndarray:
+    """NaiveSIFT.py:77-88: clipped window maximum, window half = ksize // 2."""
+    R = _f32c(R)
+    H, W = R.shape
+    out = np.empty_like(R)
+    lib().orc_maxpool(_p(R), H, W, ksize // 2, _p(out))
+    return out
+
+
+def resize(img: np.ndarray, w: int, h: int) -> np.ndarray:
+    """ScaleRotInvSIFT.py:114: cv2.resize(img, (w, h)) with the default
+    INTER_LINEAR (2x2 mean at an exact halving, IPP bilinear otherwise)."""
+    img = _f32c(img)
+    H, W = img.shape
+    out = np.empty((h, w), np.float32)
+    if W == 2 * w and H == 2 * h:
+        lib().orc_resize_half(_p(img), H, W, _p(out))
+    else:
+        lib().orc_resize_bilinear(_p(img), H, W, _p(out), h, w)
+    return out
+
+
+def build_pyramid(img: np.ndarray, levels: int, factor) -> list:
+    """ScaleRotInvSIFT.py:109-115 (_build_image_pyramid)."""
+    pyr = [_f32c(img)]
+    for i in range(1, levels):
+        prev = pyr[i - 1]
+        pyr.append(resize(prev, int(prev.shape[1] / factor), int(prev.shape[0] / factor)))
+    return pyr
+
+
+# --------------------------------------------------------------------------
+# Harris interest points (NaiveSIFT.py:54-120)
+# --------------------------------------------------------------------------
+
+def harris_candidates(img: np.ndarray, ksize: int = 7, gaussian_size: int = 7, sigma: float = 5,
+                      alpha: float = 0.05):
+    """NaiveSIFT.py:60-97: (y, x, conf, R, median) of every selected pixel in
+    row-major order, before top-k."""
+    R = harris_response(img, gaussian_size, sigma, alpha)
+    R_maxpool = maxpool(R, ksize).astype(np.float64)      # :82 np.zeros -> float64
+    median_R = np.median(R)                               # :91
+    R_maxpool[R < median_R] = 0                           # :92
+    y, x = np.where(R == R_maxpool)                       # :95-96
+    return y, x, R[y, x], R, median_R
+
+
+def canonical_desc_order(conf: np.ndarray, lin: np.ndarray) -> np.ndarray:
+    """Order by confidence descending, ties by row-major pixel index ascending.
+    The reference's argsort()[::-1] is an unstable sort, so the order inside a
+    group of bit-equal confidences is implementation-defined there; this is the
+    canonical representative both the oracle and the CUDA path emit."""
+    return np.lexsort((lin, -conf.astype(np.float64)))
+
+
+def harris_interest_points(img: np.ndarray, k: int, feature_width: int, ksize: int = 7,
+                           gaussian_size: int = 7, sigma: float = 5, alpha: float = 0.05):
+    """NaiveSIFT.py:54-120 (_find_harris_interest_points) -> x, y, conf."""
+    img = _f32c(img)
+    H, W = img.shape
+    y, x, conf, _, _ = harris_candidates(img, ksize, gaussian_size, sigma, alpha)
+    order = canonical_desc_order(conf, y.astype(np.int64) * W + x)[:k]    # :100
+    y, x, c = y[order], x[order], conf[order]
+    hw = feature_width // 2                                               # :105
+    keep = (y >= hw) & (y < H - hw) & (x >= hw) & (x < W - hw)            # :108
+    # :115 re-sorts an already descending list; canonical order is unchanged
+    return x[keep], y[keep], c[keep]
+
+
+# --------------------------------------------------------------------------
+# descriptors
+# --------------------------------------------------------------------------
+
+def _cells_descriptor(feat_magn: np.ndarray, feat_orient: np.ndarray) -> np.ndarray:
+    """NaiveSIFT.py:147-171 / ScaleRotInvSIFT.py:68-85: 4x4 cells of 4x4 pixels,
+    8-bin weighted histograms, L2 normalise, element-wise sqrt -> (128,) f32."""
+    edges = np.linspace(-np.pi, np.pi, 9)
+    wgh = []
+    for r in range(4):
+        for c in range(4):
+            pm = feat_magn[r * 4:(r + 1) * 4, c * 4:(c + 1) * 4]
+            po = feat_orient[r * 4:(r + 1) * 4, c * 4:(c + 1) * 4]
+            wgh.append(np.histogram(po.flatten(), bins=edges, weights=pm.flatten())[0])
+    wgh = np.vstack(wgh).reshape(128, 1)
+    nrm = np.linalg.norm(wgh)
+    if nrm > 0:
+        wgh = wgh / nrm
+    return np.sqrt(wgh).reshape(128).astype(np.float32)
+
+
+def dominant_orientation(feat_magn: np.ndarray, feat_orient: np.ndarray):
+    """ScaleRotInvSIFT.py:24-31: 36-bin weighted histogram, first-max bin centre
+    (float64).  Also returns the histogram for tie diagnostics."""
+    bins = np.linspace(-np.pi, np.pi, 37)
+    hist, _ = np.histogram(feat_orient, bins=bins, weights=feat_magn)
+    centers = (bins[:-1] + bins[1:]) / 2
+    return centers[np.argmax(hist)], hist
+
+
+def sift_descriptors(img: np.ndarray, X: np.ndarray, Y: np.ndarray, feature_width: int,
+                     rotation_invariant: bool = True, return_aux: bool = False):
+    """ScaleRotInvSIFT.py:33-87 (rotation_invariant) / NaiveSIFT.py:122-173.
+
+    Returns an (n, 128) float32 array for every n, including n == 0 and
+    n == 1 where the reference's np.squeeze collapses the shape (a degenerate
+    level)."""
+    img = _f32c(img)
+    assert img.ndim == 2, 'Image must be grayscale'
+    Ix, Iy = image_gradients(img)
+    magn = np.sqrt(Ix ** 2 + Iy ** 2)
+    orient = np.arctan2(Iy, Ix)
+    hw = feature_width // 2
+    out = np.zeros((len(X), 128), np.float32)
+    aux = []
+    for i in range(len(X)):
+        x, y = int(X[i]), int(Y[i])
+        fm = magn[y - hw + 1:y + hw + 1, x - hw + 1:x + hw + 1]
+        fo = orient[y - hw + 1:y + hw + 1, x - hw + 1:x + hw + 1]
+        if rotation_invariant:
+            dom, hist = dominant_orientation(fm, fo)
+            fo = fo - dom        # float32 array - np.float64 scalar -> float64
+            if return_aux:
+                aux.append((dom, hist))
+        out[i] = _cells_descriptor(fm, fo)
+    return (out, aux) if return_aux else out
+
+
+# --------------------------------------------------------------------------
+# reference-shaped classes
+# --------------------------------------------------------------------------
+
+class NaiveSIFT:
+    """FeatureExtractor/SIFT/NaiveSIFT.py:9-52."""
+
+    def __init__(self, image_bw: np.ndarray, extractor_params: Optional[dict] = None):
+        p = extractor_params or {}
+        self.image = image_bw
+        self.num_interest_points = p.get('num_interest_points', 2500)
+        self._ksize = p.get('ksize', 7)
+        self._gaussian_size = p.get('gaussian_size', 7)
+        self._sigma = p.get('sigma', 5)
+        self._alpha = p.get('alpha', 0.05)
+        self._feature_width = p.get('feature_width', 16)
+
+    def _harris(self, img, k, fw):
+        return harris_interest_points(img, k, fw, self._ksize, self._gaussian_size,
+                                      self._sigma, self._alpha)
+
+    def detect_keypoints(self):
+        self._X, self._Y, self.confidences = self._harris(
+            self.image, self.num_interest_points, self._feature_width)
+        return self._X, self._Y
+
+    def extract_descriptors(self):
+        if not hasattr(self, '_X') or not hasattr(self, '_Y'):
+            raise RuntimeError("Keypoints not detected. Call detect_keypoints() before extract_descriptors().")
+        self.descriptors = sift_descriptors(self.image, self._X, self._Y, self._feature_width,
+                                            rotation_invariant=False)
+        return self.descriptors
+
+
+class ScaleRotInvSIFT(NaiveSIFT):
+    """FeatureExtractor/SIFT/ScaleRotInvSIFT.py:8-115."""
+
+    def __init__(self, image_bw: np.ndarray, extractor_params: Optional[dict] = None):
+        super().__init__(image_bw, extractor_params)
+        p = extractor_params or {}
+        self._pyramid_level = p.get('pyramid_level', 4)
+        self._pyramid_scale_factor = p.get('pyramid_scale_factor', 2)
+        self._img_pyramid = build_pyramid(self.image, self._pyramid_level, self._pyramid_scale_factor)
+        self.compute(self.num_interest_points)
+
+    def detect_keypoints(self):
+        return self._X, self._Y
+
+    def extract_descriptors(self):
+        return self._feature_vec
+
+    def compute(self, k: int):
+        """ScaleRotInvSIFT.py:89-107."""
+        scaled_k = int(k / self._pyramid_level)
+        X, Y, F, L, LX, LY, C = [], [], [], [], [], [], []
+        for level, img in enumerate(self._img_pyramid):
+            scale = self._pyramid_scale_factor ** level
+            fw = max(int(self._feature_width / scale), 3)
+            x, y, c = self._harris(img, scaled_k, fw)
+            feat = sift_descriptors(img, x, y, fw, rotation_invariant=True)
+            X.extend((x * scale).astype(int))
+            Y.extend((y * scale).astype(int))
+            F.extend(feat)
+            L.extend([level] * len(x)); LX.extend(x); LY.extend(y); C.extend(c)
+        self._X = np.array(X)
+        self._Y = np.array(Y)
+        self._feature_vec = np.array(F)
+        # extras (not in the reference API) for parity diagnostics
+        self.levels = np.array(L, dtype=np.int64)
+        self.level_x = np.array(LX, dtype=np.int64)
+        self.level_y = np.array(LY, dtype=np.int64)
+        self.confidences = np.array(C, dtype=np.float32)
+
+
+class NNRatioFeatureMatcher:
+    """FeatureMatcher/NNRatioFeatureMatcher.py:4-60."""
+
+    def __init__(self, ratio_threshold=0.8):
+        self.ratio_threshold = ratio_threshold
+
+    def top2(self, features1: np.ndarray, features2: np.ndarray):
+        f1, f2 = _f32c(features1), _f32c(features2)
+        n1, D = f1.shape
+        n2 = f2.shape[0]
+        idx0 = np.empty(n1, np.int64)
+        d0 = np.empty(n1, np.float32)
+        d1 = np.empty(n1, np.float32)
+        lib().orc_match_top2(_p(f1), 0, n1, _p(f2), n2, D,
+                             idx0.ctypes.data_as(_i64p), _p(d0), _p(d1))
+        return idx0, d0, d1
+
+    def match_features_ratio_test(self, features1: np.ndarray, features2: np.ndarray):
+        """NNRatioFeatureMatcher.py:8-60.  Matches are ordered by confidence
+        ascending, ties by features1 index ascending (the reference's argsort
+        leaves tie order implementation-defined)."""
+        if features2.shape[0] < 2:
+            raise IndexError("index 1 is out of bounds for axis 0 with size %d" % features2.shape[0])
+        idx0, d0, d1 = self.top2(features1, features2)
+        ok = d1 > 0                                                     # :46
+        with np.errstate(divide='ignore', invalid='ignore'):
+            nndr = d0 / d1                                              # :47 float32
+        ok &= nndr <= np.float32(self.ratio_threshold)                  # :49 (NEP 50: f32 compare)
+        rows = np.nonzero(ok)[0]
+        if len(rows) == 0:                                              # :53-58 on empty lists
+            return np.array([]), np.array([])
+        conf = nndr[rows]
+        order = np.lexsort((rows, conf))
+        matches = np.stack([rows, idx0[rows]], axis=1).astype(np.int64)
+        return matches[order], conf[order].astype(np.float32)
+
+
+def dist_matrix(features1: np.ndarray, features2: np.ndarray) -> np.ndarray:
+    """NNRatioFeatureMatcher.py:31-34, full float32 matrix (small cases)."""
+    f1, f2 = _f32c(features1), _f32c(features2)
+    out = np.empty((f1.shape[0], f2.shape[0]), np.float32)
+    lib().orc_dist_matrix(_p(f1), f1.shape[0], _p(f2), f2.shape[0], f1.shape[1], _p(out))
+    return out

@@ -1,0 +1,103 @@
+"""Seeded synthetic inputs for the feature hot path.
+
+Everything here is plain element-wise numpy in float64 with a fixed operation
+order, so the same seed yields the same bytes on every x86 host (no BLAS, no
+OpenCV, no reduction whose order depends on the SIMD width).  Used by the
+tests, ``bench.py`` and the golden-vector generator.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def _gauss_taps(sigma: float) -> np.ndarray:
+    r = int(np.ceil(4.0 * sigma))
+    t = np.arange(-r, r + 1, dtype=np.float64)
+    k = np.exp(-(t * t) / (2.0 * sigma * sigma))
+    s = 0.0
+    for v in k:            # fixed-order sum
+        s += float(v)
+    return k / s
+
+
+def _blur_axis(a: np.ndarray, taps: np.ndarray, axis: int) -> np.ndarray:
+    r = len(taps) // 2
+    pad = [(0, 0), (0, 0)]
+    pad[axis] = (r, r)
+    p = np.pad(a, pad, mode="reflect")
+    out = np.zeros_like(a)
+    n = a.shape[axis]
+    for i, w in enumerate(taps):
+        sl = [slice(None), slice(None)]
+        sl[axis] = slice(i, i + n)
+        out += w * p[tuple(sl)]
+    return out
+
+
+def synth_image(h: int, w: int, seed: int, sigma: float = 2.0) -> np.ndarray:
+    """Uniform noise -> Gaussian blur (sigma 2) -> min-max normalise to [0,1].
+    float32 (h, w), generic enough that Harris responses do not tie."""
+    rng = np.random.default_rng(seed)
+    a = rng.random((h, w), dtype=np.float64)
+    taps = _gauss_taps(sigma)
+    a = _blur_axis(_blur_axis(a, taps, 0), taps, 1)
+    lo, hi = a.min(), a.max()
+    return ((a - lo) / (hi - lo)).astype(np.float32)
+
+
+def second_view(img: np.ndarray, seed: int, noise: float = 0.005) -> np.ndarray:
+    """Affine warp [[1, .02, 3.5], [-.02, 1, -2.25]] (bilinear, reflect border)
+    plus N(0, noise) -- the second camera of the synthetic two-view pair."""
+    h, w = img.shape
+    a = img.astype(np.float64)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    sx = xx + 0.02 * yy + 3.5
+    sy = -0.02 * xx + yy - 2.25
+
+    def refl(v, n):
+        v = np.abs(v)
+        period = 2.0 * (n - 1)
+        v = np.mod(v, period)
+        return np.where(v > n - 1, period - v, v)
+
+    sx, sy = refl(sx, w), refl(sy, h)
+    x0 = np.minimum(np.floor(sx).astype(np.int64), w - 2)
+    y0 = np.minimum(np.floor(sy).astype(np.int64), h - 2)
+    fx, fy = sx - x0, sy - y0
+    top = a[y0, x0] * (1 - fx) + a[y0, x0 + 1] * fx
+    bot = a[y0 + 1, x0] * (1 - fx) + a[y0 + 1, x0 + 1] * fx
+    out = top * (1 - fy) + bot * fy
+    rng = np.random.default_rng(seed)
+    out = out + rng.normal(0.0, noise, size=out.shape)
+    return np.clip(out, 0.0, 1.0).astype(np.float32)
+
+
+def _rootsift_like(h: np.ndarray) -> np.ndarray:
+    """sqrt(l2normalise(h)) row-wise in float64 with a fixed-order norm."""
+    sq = h * h
+    s = np.zeros(h.shape[0], np.float64)
+    for j in range(h.shape[1]):
+        s += sq[:, j]
+    return np.sqrt(h / np.sqrt(s)[:, None])
+
+
+def synth_descriptor_base(n: int, seed: int = 12345, dim: int = 128) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    return rng.gamma(0.5, 1.0, size=(n, dim))
+
+
+def synth_descriptors(n: int, image_id: int, base: np.ndarray | None = None,
+                      planted: float = 0.5, noise: float = 0.05, dim: int = 128) -> np.ndarray:
+    """Config-5 style descriptors: a `planted` fraction of rows are noisy copies
+    of a shared base set (so true matches exist between images), the rest are
+    fresh Gamma(0.5) rows; RootSIFT-shaped (non-negative, sqrt of an
+    L2-normalised histogram).  float32 (n, dim)."""
+    if base is None:
+        base = synth_descriptor_base(n, dim=dim)
+    rng = np.random.default_rng(1000003 * (image_id + 1))
+    h = rng.gamma(0.5, 1.0, size=(n, dim))
+    npl = int(n * planted)
+    rows = rng.permutation(n)[:npl]
+    src = rng.permutation(base.shape[0])[:npl]
+    h[rows] = base[src] + np.abs(rng.normal(0.0, noise, size=(npl, dim)))
+    return _rootsift_like(h).astype(np.float32)
