@@ -1,0 +1,186 @@
+/*
+ * sfmb200.h -- C ABI of libsfmb200.so, the B200 (sm_100a) implementation of
+ * the SfmFromScratch feature hot path.
+ *
+ * The reference is pure Python and has no FFI; the interfaces this boundary
+ * replaces are the Python methods a binding would route here (paths relative
+ * to the reference root):
+ *
+ *   sfm_extract_batch        FeatureExtractor/SIFT/ScaleRotInvSIFT.py:9-16,89-115
+ *                            (ScaleRotInvSIFT.__init__ -> _build_image_pyramid +
+ *                            compute) and, with rotation_invariant = 0 and
+ *                            pyramid_level = 1, FeatureExtractor/SIFT/
+ *                            NaiveSIFT.py:42-52 (detect_keypoints +
+ *                            extract_descriptors)
+ *   sfm_harris_response      FeatureExtractor/SIFT/NaiveSIFT.py:60-74 (R map only;
+ *                            exposed for parity tests)
+ *   sfm_match_ratio          FeatureMatcher/NNRatioFeatureMatcher.py:8-60
+ *                            (match_features_ratio_test)
+ *   sfm_match_ratio_batch    the same method over a list of image pairs (the
+ *                            reference loops over consecutive pairs at
+ *                            Runner.py:183-191,344-347)
+ *
+ * Conventions
+ *   - Every pointer marked "dev" is CUDA device memory owned by the caller (the
+ *     Python host side allocates it as torch tensors); the library never frees
+ *     caller memory and keeps no reference after the call is enqueued, except
+ *     for `workspace`, which must stay alive until the stream has drained.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it
+ *     and the calls do not synchronise unless stated.
+ *   - Return value: 0 on success, a negative SfmStatus otherwise;
+ *     sfm_last_error(ctx) returns a description for the calling thread.
+ *   - A context may be used from several host threads concurrently (the
+ *     reference calls the extractor from an 8-thread pool, Runner.py:186-191):
+ *     calls carry their own workspace and stream, the context holds only
+ *     immutable device properties and a mutex-protected error slot.
+ *   - There is no CPU fallback: without a CUDA device every entry point other
+ *     than sfm_version / sfm_last_error fails with SFM_ERR_CUDA.
+ */
+#ifndef SFMB200_H_
+#define SFMB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SFM_EXPORT __attribute__((visibility("default")))
+#else
+#define SFM_EXPORT
+#endif
+
+#define SFM_API_VERSION 1
+#define SFM_DESC_DIM 128      /* descriptor length (4 x 4 cells x 8 bins) */
+#define SFM_MAX_LEVELS 8      /* pyramid_level upper bound */
+#define SFM_MAX_GAUSS 11      /* gaussian_size upper bound (odd); cv2.filter2D
+                                 switches to a DFT path at 11x11 and above in
+                                 area >= 130, which the reference's defaults
+                                 never reach */
+
+typedef enum SfmStatus {
+    SFM_OK = 0,
+    SFM_ERR_BAD_ARG = -1,
+    SFM_ERR_CUDA = -2,
+    SFM_ERR_WORKSPACE = -3,   /* workspace_bytes smaller than the query says */
+    SFM_ERR_CAPACITY = -4,    /* reported by sfm_extract_status: a per-level
+                                 candidate buffer overflowed (plateau image);
+                                 call again with cand_full = 1 */
+    SFM_ERR_UNSUPPORTED = -5
+} SfmStatus;
+
+typedef struct SfmCtx SfmCtx;
+
+/* Extractor parameters: the keys of the reference's extractor_params dict
+ * (main.py:19-28; FeatureExtractor.py:11; NaiveSIFT.py:35-39;
+ * ScaleRotInvSIFT.py:12-13) with the same defaults. */
+typedef struct SfmExtractParams {
+    int32_t num_interest_points;   /* 2500 */
+    int32_t ksize;                 /* 7: NMS window = 2*(ksize/2)+1 */
+    int32_t gaussian_size;         /* 7, odd, <= SFM_MAX_GAUSS */
+    double  sigma;                 /* 5 */
+    double  alpha;                 /* 0.05 (applied as float32) */
+    int32_t feature_width;         /* 16 */
+    int32_t pyramid_level;         /* 4; 1 for NaiveSIFT */
+    double  pyramid_scale_factor;  /* 2 */
+    int32_t rotation_invariant;    /* 1: ScaleRotInvSIFT descriptors, 0: NaiveSIFT */
+    int32_t split_k_by_level;      /* 1: per-level k = int(k / levels)
+                                      (ScaleRotInvSIFT.py:90); 0: k */
+    int32_t cand_full;             /* 0: candidate buffers sized by the NMS
+                                      density bound; 1: one slot per pixel */
+    /* Optional HOST pointer to gaussian_size^2 float32 window weights in
+     * row-major order.  NULL: the library evaluates NaiveSIFT.py:175-199 in
+     * double precision with libm exp().  The Python host side passes the
+     * numpy-computed kernel so the weights are the reference's to the bit. */
+    const float* gauss_weights;
+} SfmExtractParams;
+
+SFM_EXPORT int  sfm_version(void);
+SFM_EXPORT int  sfm_ctx_create(int device, SfmCtx** out);
+SFM_EXPORT void sfm_ctx_destroy(SfmCtx* ctx);
+SFM_EXPORT const char* sfm_last_error(SfmCtx* ctx);
+/* Number of SMs of the context's device (grid sizing for callers/tests). */
+SFM_EXPORT int  sfm_ctx_sm_count(SfmCtx* ctx);
+
+/* Fill p with the reference defaults. */
+SFM_EXPORT void sfm_extract_default_params(SfmExtractParams* p);
+
+/* Upper bound on keypoints per image for these parameters
+ * (levels * per-level k): the row capacity the output arrays need. */
+SFM_EXPORT int  sfm_extract_max_keypoints(const SfmExtractParams* p);
+
+/* Workspace size in bytes for a batch of B images of H x W. */
+SFM_EXPORT size_t sfm_extract_workspace_bytes(int B, int H, int W, const SfmExtractParams* p);
+
+/*
+ * Extract keypoints and descriptors for B grayscale float32 images
+ * (images_dev: [B][H][W], row stride W).  Outputs, all dev, capacity `cap`
+ * rows per image (cap >= sfm_extract_max_keypoints):
+ *   x_out, y_out   [B][cap] int32  level-0 coordinates, (x * scale).astype(int)
+ *   lx_out, ly_out [B][cap] int32  coordinates inside the pyramid level (may be NULL)
+ *   level_out      [B][cap] int32  pyramid level (may be NULL)
+ *   conf_out       [B][cap] float  Harris response (may be NULL)
+ *   desc_out       [B][cap][128] float
+ *   count_out      [B] int32       keypoints written for each image
+ * Keypoints are ordered as the reference orders them: level by level, inside
+ * a level by response descending (ties: row-major pixel index ascending).
+ */
+SFM_EXPORT int sfm_extract_batch(SfmCtx* ctx, void* stream, const float* images_dev, int B, int H, int W,
+                      const SfmExtractParams* p, void* workspace_dev, size_t workspace_bytes,
+                      int32_t* x_out, int32_t* y_out, int32_t* lx_out, int32_t* ly_out,
+                      int32_t* level_out, float* conf_out, float* desc_out, int32_t* count_out,
+                      int cap);
+
+/* After the stream has been synchronised: 0, or SFM_ERR_CAPACITY when a
+ * candidate buffer of the last sfm_extract_batch call on this workspace
+ * overflowed (reads one flag word back from the workspace). */
+SFM_EXPORT int sfm_extract_status(SfmCtx* ctx, void* stream, const void* workspace_dev);
+
+/* Harris response map of one H x W image (NaiveSIFT.py:60-74): r_out [H][W]. */
+SFM_EXPORT int sfm_harris_response(SfmCtx* ctx, void* stream, const float* image_dev, int H, int W,
+                        const SfmExtractParams* p, float* r_out);
+
+/* ---- matching ---------------------------------------------------------- */
+
+typedef enum SfmMatchMode {
+    SFM_MATCH_AUTO = 0,     /* tcgen05 fp16 candidate pass + exact float32
+                               re-check (+ exact scan of rows whose error bound
+                               cannot certify the candidates) */
+    SFM_MATCH_EXACT = 1     /* exact float32 scan of every row (validation) */
+} SfmMatchMode;
+
+/* Workspace bytes for matching n_sets descriptor sets of at most nmax rows over
+ * n_pairs pairs. */
+SFM_EXPORT size_t sfm_match_workspace_bytes(int n_sets, int nmax, int n_pairs);
+
+/*
+ * One pair.  f1_dev [n1][128], f2_dev [n2][128] float32 row-major, n2 >= 2.
+ * Outputs (dev): match_out [cap][2] int32 (index into f1, index into f2),
+ * conf_out [cap] float32 (d_nearest / d_second), count_out [1] int32, ordered
+ * by confidence ascending (ties: f1 index ascending).  cap >= n1 always fits.
+ */
+SFM_EXPORT int sfm_match_ratio(SfmCtx* ctx, void* stream, const float* f1_dev, int n1, const float* f2_dev,
+                    int n2, int dim, float ratio_threshold, int mode, void* workspace_dev,
+                    size_t workspace_bytes, int32_t* match_out, float* conf_out,
+                    int32_t* count_out, int cap);
+
+/*
+ * Many pairs over a table of descriptor sets.  desc_dev [n_sets][nmax][128]
+ * float32, counts_dev [n_sets] int32 (rows used per set, each >= 2 when the set
+ * is used as a train set), pairs_dev [n_pairs][2] int32 (query set, train set).  Outputs as above with a leading
+ * pair dimension: match_out [n_pairs][cap][2], conf_out [n_pairs][cap],
+ * count_out [n_pairs].  stats_out (dev, may be NULL) [n_pairs][2] int32:
+ * rows re-scanned exactly, candidate groups re-checked.
+ */
+SFM_EXPORT int sfm_match_ratio_batch(SfmCtx* ctx, void* stream, const float* desc_dev,
+                          const int32_t* counts_dev, int n_sets, int nmax,
+                          const int32_t* pairs_dev, int n_pairs, float ratio_threshold, int mode,
+                          void* workspace_dev, size_t workspace_bytes, int32_t* match_out,
+                          float* conf_out, int32_t* count_out, int32_t* stats_out, int cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SFMB200_H_ */

@@ -1,0 +1,118 @@
+"""ctypes binding of libsfmb200.so (C ABI: include/sfmb200.h).
+
+The library is the only compute path: if it is missing, or no B200 is
+visible, every operation raises -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsfmb200.so")
+
+SFM_OK = 0
+SFM_ERR_BAD_ARG = -1
+SFM_ERR_CUDA = -2
+SFM_ERR_WORKSPACE = -3
+SFM_ERR_CAPACITY = -4
+SFM_ERR_UNSUPPORTED = -5
+SFM_MATCH_AUTO = 0
+SFM_MATCH_EXACT = 1
+DESC_DIM = 128
+
+# every symbol include/sfmb200.h declares
+EXPORTS = [
+    "sfm_version", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_error", "sfm_ctx_sm_count",
+    "sfm_extract_default_params", "sfm_extract_max_keypoints", "sfm_extract_workspace_bytes",
+    "sfm_extract_batch", "sfm_extract_status", "sfm_harris_response",
+    "sfm_match_workspace_bytes", "sfm_match_ratio", "sfm_match_ratio_batch",
+]
+
+
+class SfmExtractParams(C.Structure):
+    _fields_ = [
+        ("num_interest_points", C.c_int32),
+        ("ksize", C.c_int32),
+        ("gaussian_size", C.c_int32),
+        ("sigma", C.c_double),
+        ("alpha", C.c_double),
+        ("feature_width", C.c_int32),
+        ("pyramid_level", C.c_int32),
+        ("pyramid_scale_factor", C.c_double),
+        ("rotation_invariant", C.c_int32),
+        ("split_k_by_level", C.c_int32),
+        ("cand_full", C.c_int32),
+        ("gauss_weights", C.POINTER(C.c_float)),
+    ]
+
+
+_lib = None
+_lib_lock = threading.Lock()
+_ctxs = {}
+
+
+def load_library() -> C.CDLL:
+    """dlopen libsfmb200.so and declare its prototypes.  Raises if absent."""
+    global _lib
+    with _lib_lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(sfmfromscratch_b200 has no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        vp, i32p, fp = C.c_void_p, C.c_void_p, C.c_void_p       # device pointers travel as integers
+        PP = C.POINTER(SfmExtractParams)
+        L.sfm_version.restype = C.c_int
+        L.sfm_ctx_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.sfm_ctx_destroy.argtypes = [C.c_void_p]
+        L.sfm_ctx_destroy.restype = None
+        L.sfm_last_error.argtypes = [C.c_void_p]
+        L.sfm_last_error.restype = C.c_char_p
+        L.sfm_ctx_sm_count.argtypes = [C.c_void_p]
+        L.sfm_extract_default_params.argtypes = [PP]
+        L.sfm_extract_default_params.restype = None
+        L.sfm_extract_max_keypoints.argtypes = [PP]
+        L.sfm_extract_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int, PP]
+        L.sfm_extract_workspace_bytes.restype = C.c_size_t
+        L.sfm_extract_batch.argtypes = [vp, vp, fp, C.c_int, C.c_int, C.c_int, PP, vp, C.c_size_t,
+                                        i32p, i32p, i32p, i32p, i32p, fp, fp, i32p, C.c_int]
+        L.sfm_extract_status.argtypes = [vp, vp, vp]
+        L.sfm_harris_response.argtypes = [vp, vp, fp, C.c_int, C.c_int, PP, fp]
+        L.sfm_match_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
+        L.sfm_match_workspace_bytes.restype = C.c_size_t
+        L.sfm_match_ratio.argtypes = [vp, vp, fp, C.c_int, fp, C.c_int, C.c_int, C.c_float, C.c_int, vp,
+                                      C.c_size_t, i32p, fp, i32p, C.c_int]
+        L.sfm_match_ratio_batch.argtypes = [vp, vp, fp, i32p, C.c_int, C.c_int, i32p, C.c_int, C.c_float,
+                                            C.c_int, vp, C.c_size_t, i32p, fp, i32p, i32p, C.c_int]
+        _lib = L
+        return L
+
+
+class SfmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libsfmb200 error {code}: {msg}")
+        self.code = code
+
+
+def get_ctx(device: int = 0) -> int:
+    """One context per (process, device).  Raises RuntimeError without a B200."""
+    L = load_library()
+    with _lib_lock:
+        if device in _ctxs:
+            return _ctxs[device]
+        h = C.c_void_p()
+        rc = L.sfm_ctx_create(device, C.byref(h))
+        if rc != SFM_OK:
+            msg = L.sfm_last_error(None).decode()
+            raise SfmError(rc, msg)
+        _ctxs[device] = h.value
+        return h.value
+
+
+def check(rc: int, ctx: int) -> None:
+    if rc != SFM_OK:
+        raise SfmError(rc, load_library().sfm_last_error(ctx).decode())

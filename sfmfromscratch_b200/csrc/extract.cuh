@@ -1,0 +1,62 @@
+// extract.cuh -- plan / workspace layout shared by the extraction kernels.
+#pragma once
+#include "common.cuh"
+
+#define SFM_HIST1_BINS 4096      // pass 1: key >> 20
+#define SFM_HIST2_BINS 4096      // pass 2: (key >> 8) & 0xfff
+#define SFM_HIST3_BINS 256       // pass 3: key & 0xff
+#define SFM_MAX_FW 32            // feature_width / window side upper bound
+
+struct SegState {                // one per (image, level)
+    uint32_t prefix[2];          // radix-select prefix for the two median ranks
+    uint32_t rank[2];            // remaining rank inside the prefix bucket
+    float    median;
+    uint32_t n_cand;             // candidates appended by NMS (may exceed cap)
+    uint32_t n_sel;              // selected, border-valid keypoints
+    uint32_t pad;
+};
+
+struct LevelInfo {
+    int H, W;
+    int fw, hw;                  // feature width at this level and fw / 2
+    int k;                       // per-level top-k
+    int cand_cap;                // candidate slots
+    int resize_mode;             // 0: level 0, 1: exact 2x2 mean, 2: bilinear
+    int sel_off;                 // offset of this level inside the per-image sel block
+    long long img_off;           // float offset inside the per-image pyramid block (level >= 1)
+    long long r_off;             // float offset inside the per-image R block
+    long long cand_off;          // u64 offset inside the per-image candidate block
+    double scale;                // pyramid_scale_factor ** level
+    double inv_x, inv_y;         // src/dst size ratios for the bilinear resize
+};
+
+struct ExtractPlan {
+    int B, L, H0, W0;
+    int nms_half, G, rot, pad0;
+    float alpha;
+    int sel_stride;              // sum of per-level k
+    long long pyr_stride, r_stride, cand_stride;
+    LevelInfo lv[SFM_MAX_LEVELS];
+    // workspace
+    const float* images;
+    float* pyr;
+    float* R;
+    uint32_t* hist1;             // [S][4096]
+    uint32_t* hist2;             // [S][2][4096]
+    uint32_t* hist3;             // [S][2][256]
+    SegState* seg;               // [S]
+    unsigned long long* cand;    // [B][cand_stride]
+    unsigned long long* sel;     // [B][sel_stride]
+    int* flags;                  // [0]: candidate overflow
+    double e9[9];                // np.linspace(-pi, pi, 9)
+    double e37[37];              // np.linspace(-pi, pi, 37)
+};
+
+struct GaussWeights { float w[SFM_MAX_GAUSS * SFM_MAX_GAUSS]; };
+
+struct ExtractOut {
+    int32_t *x, *y, *lx, *ly, *level;
+    float *conf, *desc;
+    int32_t* count;
+    int cap;
+};

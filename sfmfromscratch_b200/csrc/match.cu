@@ -1,0 +1,596 @@
+// match.cu -- NN-ratio matcher (NNRatioFeatureMatcher.py:8-60) on sm_100a.
+//
+//   k_match_setup    set / pair tables
+//   k_match_prep     float32 -> fp16 copy, |b|^2, rounding-residual norms
+//   k_match_tc       (match_tc.cu) tcgen05 fp16 GEMM tiles, fused top-4 groups
+//   k_match_recheck  exact float32 distances (numpy summation order) of the
+//                    candidate groups + error-bound certificate
+//   k_match_exact    exact tile scan of rows the certificate rejected
+//                    (all rows in SFM_MATCH_EXACT mode), k_match_merge
+//   k_match_emit     d1 > 0, d0/d1 <= thr            (:46-51)
+//   k_match_sort     order by confidence             (:56-58)
+//
+// "Exact" means the reference's float32 arithmetic: t = a - b, t * t, numpy's
+// pairwise sum over 128 contiguous values (8 strided accumulators and the tree
+// ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7))), sqrt, divide.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "match.cuh"
+
+int launch_match_tc(SfmCtx* ctx, cudaStream_t st, const MatchPlan& P);   // match_tc.cu
+
+// ------------------------------------------------------------------ setup / prep
+
+__global__ void k_match_setup(const __grid_constant__ MatchPlan P) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (P.desc == nullptr) {
+        if (t == 0) {
+            P.set_ptr[0] = P.f1; P.set_ptr[1] = P.f2;
+            P.set_cnt[0] = P.n1; P.set_cnt[1] = P.n2;
+            P.pairs[0] = 0; P.pairs[1] = 1;
+        }
+    } else {
+        if (t < P.n_sets) {
+            P.set_ptr[t] = P.desc + (size_t)t * P.nmax * SFM_DESC_DIM;
+            int c = P.counts_in[t];
+            P.set_cnt[t] = c < 0 ? 0 : (c > P.nmax ? P.nmax : c);
+        }
+        if (t < P.n_pairs) {
+            P.pairs[2 * t] = P.pairs_in[2 * t];
+            P.pairs[2 * t + 1] = P.pairs_in[2 * t + 1];
+        }
+    }
+}
+
+// Warp per row: fp16 copy for the tensor-core pass, |b|^2 and the norms the
+// re-check's error bound needs.
+__global__ void __launch_bounds__(256) k_match_prep(const __grid_constant__ MatchPlan P) {
+    const int s = blockIdx.y;
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= P.nmax_pad) return;
+    const int cnt = P.set_cnt[s];
+    const size_t orow = (size_t)s * P.nmax_pad + r;
+    __half2* out = reinterpret_cast<__half2*>(P.h16 + orow * SFM_DESC_DIM + lane * 4);
+    if (r >= cnt) {
+        out[0] = __floats2half2_rn(0.f, 0.f);
+        out[1] = __floats2half2_rn(0.f, 0.f);
+        if (lane == 0) { P.nb[orow] = MT_SENTINEL; P.hatn[orow] = 0.f; P.resn[orow] = 0.f; }
+        return;
+    }
+    const float4 v = *reinterpret_cast<const float4*>(P.set_ptr[s] + (size_t)r * SFM_DESC_DIM + lane * 4);
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    out[0] = h01; out[1] = h23;
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    float nb = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    float hn = f01.x * f01.x + f01.y * f01.y + f23.x * f23.x + f23.y * f23.y;
+    float e0 = v.x - f01.x, e1 = v.y - f01.y, e2 = v.z - f23.x, e3 = v.w - f23.y;
+    float rn = e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+    for (int o = 16; o > 0; o >>= 1) {
+        nb += __shfl_xor_sync(0xffffffffu, nb, o);
+        hn += __shfl_xor_sync(0xffffffffu, hn, o);
+        rn += __shfl_xor_sync(0xffffffffu, rn, o);
+    }
+    if (lane == 0) {
+        const float hs = sqrtf(hn), rs = sqrtf(rn);
+        P.nb[orow] = nb; P.hatn[orow] = hs; P.resn[orow] = rs;
+        // non-negative floats order like their bit patterns
+        atomicMax(reinterpret_cast<int*>(P.setmax + 4 * s + 0), __float_as_int(hs));
+        atomicMax(reinterpret_cast<int*>(P.setmax + 4 * s + 1), __float_as_int(rs));
+        atomicMax(reinterpret_cast<int*>(P.setmax + 4 * s + 2), __float_as_int(nb));
+    }
+}
+
+// ------------------------------------------------------------------ exact arithmetic
+
+struct Top2 { float d0; int i0; float d1; };
+
+__device__ __forceinline__ Top2 top2_merge(Top2 a, Top2 b) {
+    const bool bwins = (b.d0 < a.d0) || (b.d0 == a.d0 && b.i0 >= 0 && (a.i0 < 0 || b.i0 < a.i0));
+    if (bwins) { Top2 t = a; a = b; b = t; }
+    a.d1 = fminf(a.d1, b.d0);
+    return a;
+}
+
+__device__ __forceinline__ void top2_push(Top2& s, float d, int j) {
+    if (d < s.d0) { s.d1 = s.d0; s.d0 = d; s.i0 = j; }
+    else if (d < s.d1) { s.d1 = d; }
+}
+
+// ------------------------------------------------------------------ re-check of tensor-core candidates
+
+// Warp per query row.  Entries of the row's candidate lists are visited in
+// increasing approximate key; each visit evaluates the 4 columns of the group
+// exactly (8 lanes per column, lane j owns numpy's accumulator r[j]).  The row
+// is certified when every unvisited or untracked column is provably farther
+// than the exact second-nearest found: approx_key + |a|^2 - E > d1^2, with E a
+// rigorous bound on |approx - exact| (fp16 rounding of both operands by
+// Cauchy-Schwarz on the residual norms, accumulation, index packing, and the
+// float32 rounding of the exact sum itself).  Uncertified rows go to the exact
+// scan.
+__global__ void __launch_bounds__(256) k_match_recheck(const __grid_constant__ MatchPlan P) {
+    const int p = blockIdx.y;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    const int qa = P.pairs[2 * p], qb = P.pairs[2 * p + 1];
+    const int n1 = P.set_cnt[qa], n2 = P.set_cnt[qb];
+    if (row >= n1 || n2 < 2) return;                       // n2 < 2: the pair emits nothing
+    const float* A = P.set_ptr[qa] + (size_t)row * SFM_DESC_DIM;
+    const float* B = P.set_ptr[qb];
+    const size_t arow = (size_t)qa * P.nmax_pad + row;
+    const double na = (double)P.nb[arow];
+    const double hat_a = (double)P.hatn[arow], res_a = (double)P.resn[arow];
+    const double mh = (double)P.setmax[4 * qb + 0], mr = (double)P.setmax[4 * qb + 1], mnb = (double)P.setmax[4 * qb + 2];
+    const double e_fp16 = 2.0 * (hat_a * mr + res_a * mh + res_a * mr);
+    const double e_acc = 2.0 * hat_a * mh * (1.0 / 262144.0);                   // 2^-18
+    const double e_ref = (na + mnb + 2.0 * sqrt(na * mnb)) * (1.0 / 524288.0);  // 2^-19 * dmax^2
+    const double e_nrm = (na + mnb) * (1.0 / 131072.0);                         // 2^-17
+    const double e_base = 1.1 * (e_fp16 + e_acc + e_ref + e_nrm) + 1e-12;
+    const double q_rel = 1.1 / 8192.0 * 2.0;                                    // packing drops 10 mantissa bits
+
+    const int E = P.n_lists * MT_TOPK;
+    const uint32_t* lists = P.cands + ((size_t)p * P.nmax_pad + row) * (size_t)E;
+    float val[4];
+    uint32_t code[4];
+    float Lmin = INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int e = lane + 32 * i;
+        val[i] = INFINITY; code[i] = 0;
+        if (e < E) {
+            const uint32_t pk = lists[e];
+            const float v = __uint_as_float(pk & ~MT_IDX_MASK);
+            if (v < MT_INVALID) {
+                val[i] = v;
+                code[i] = ((uint32_t)(e / MT_TOPK) << MT_IDX_BITS) | (pk & MT_IDX_MASK);
+                if ((e % MT_TOPK) == MT_TOPK - 1) Lmin = fminf(Lmin, v);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) Lmin = fminf(Lmin, __shfl_xor_sync(0xffffffffu, Lmin, o));
+
+    float a[16];
+    const int j = lane & 7, team = lane >> 3;
+#pragma unroll
+    for (int m = 0; m < 16; ++m) a[m] = A[8 * m + j];
+
+    Top2 best = {INFINITY, -1, INFINITY};
+    int visited = 0;
+    for (;;) {
+        // smallest unvisited entry across the warp
+        float bv = INFINITY; uint32_t bc = 0; int bi = -1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (val[i] < bv) { bv = val[i]; bc = code[i]; bi = i; }
+        float wv = bv; int wl = (bi >= 0) ? lane : 64;
+        for (int o = 16; o > 0; o >>= 1) {
+            float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+            int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+            if (ov < wv || (ov == wv && ol < wl)) { wv = ov; wl = ol; }
+        }
+        if (wl >= 32) break;                                 // nothing left
+        const double bound = (double)wv + na - (e_base + q_rel * fabs((double)wv));
+        if (bound > (double)best.d1) break;                  // the rest cannot matter
+        const uint32_t wc = __shfl_sync(0xffffffffu, bc, wl);
+        if (lane == wl) {                                    // mark visited (static indexing)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if (i == bi) val[i] = INFINITY;
+        }
+        const int list = (int)(wc >> MT_IDX_BITS);
+        const int split = list >> 1, half = list & 1;
+        const int tile = split * P.tiles_per_split + (int)((wc & MT_IDX_MASK) >> 4);
+        const int col = tile * MT_COLS + half * 64 + (int)(wc & 15u) * MT_GROUP + team;
+        const int colc = col < n2 ? col : n2 - 1;            // clamp: every lane runs the same shuffles
+        float d2;
+        {
+            const float* b = B + (size_t)colc * SFM_DESC_DIM + j;
+            float t0 = __fsub_rn(a[0], b[0]);
+            float r = __fmul_rn(t0, t0);
+#pragma unroll
+            for (int m = 1; m < 16; ++m) {
+                float tt = __fsub_rn(a[m], b[8 * m]);
+                r = __fadd_rn(r, __fmul_rn(tt, tt));
+            }
+            r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));   // (r0+r1) ...
+            r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));   // (r0+r1)+(r2+r3)
+            r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));   // full tree
+            d2 = r;
+        }
+#pragma unroll
+        for (int tm = 0; tm < 4; ++tm) {
+            const float dd = __shfl_sync(0xffffffffu, d2, tm * 8);
+            const int cc = col - team + tm;
+            if (cc < n2) top2_push(best, dd, cc);
+        }
+        ++visited;
+    }
+    const bool certified =
+        (Lmin == INFINITY) ||
+        ((double)Lmin + na - (e_base + q_rel * fabs((double)Lmin)) > (double)best.d1);
+    if (lane == 0) {
+        if (P.stats) atomicAdd(&P.stats[2 * p + 1], visited);
+        if (certified && n2 >= 2) {
+            const size_t o = (size_t)p * P.nmax + row;
+            P.res_idx[o] = best.i0; P.res_d0[o] = best.d0; P.res_d1[o] = best.d1;
+        } else {
+            const int pos = atomicAdd(&P.flag_cnt[p], 1);
+            P.flag_rows[(size_t)p * P.nmax + pos] = row;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ exact tile scan
+
+__global__ void k_flag_all(const __grid_constant__ MatchPlan P) {
+    const int p = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n1 = P.set_cnt[P.pairs[2 * p]];
+    if (i < n1) P.flag_rows[(size_t)p * P.nmax + i] = i;
+    if (i == 0) P.flag_cnt[p] = n1;
+}
+
+__global__ void k_work_scan(const __grid_constant__ MatchPlan P) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    int acc = 0;
+    for (int p = 0; p < P.n_pairs; ++p) {
+        P.work_off[p] = acc;
+        acc += ((P.flag_cnt[p] + MX_ROWS - 1) / MX_ROWS) * P.n_xchunks;
+    }
+    P.work_off[P.n_pairs] = acc;
+}
+
+// Work item = (pair, 8 flagged rows, 1024-column chunk).  Each thread walks its
+// columns with all 8 x 8 numpy accumulators in registers; the query rows are
+// broadcast from shared memory.
+__global__ void __launch_bounds__(256, 1) k_match_exact(const __grid_constant__ MatchPlan P) {
+    __shared__ __align__(16) float s_a[MX_ROWS][SFM_DESC_DIM];
+    __shared__ Top2 s_red[8][MX_ROWS];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int total = P.work_off[P.n_pairs];
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        int lo = 0, hi = P.n_pairs - 1;                        // last p with work_off[p] <= w
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (P.work_off[mid] <= w) lo = mid; else hi = mid - 1;
+        }
+        const int p = lo;
+        const int local = w - P.work_off[p];
+        const int rg = local / P.n_xchunks, ch = local - rg * P.n_xchunks;
+        const int qa = P.pairs[2 * p], qb = P.pairs[2 * p + 1];
+        const int n2 = P.set_cnt[qb];
+        const int nflag = P.flag_cnt[p];
+        const int col0 = ch * MX_COLS;
+        const int col1 = min(col0 + MX_COLS, n2);
+        __syncthreads();                                       // previous item's smem is free
+        for (int q = t; q < MX_ROWS * SFM_DESC_DIM; q += 256) {
+            const int r = q >> 7, c = q & 127;
+            const int slot = rg * MX_ROWS + r;
+            float v = 0.f;
+            if (slot < nflag) {
+                const int row = P.flag_rows[(size_t)p * P.nmax + slot];
+                v = P.set_ptr[qa][(size_t)row * SFM_DESC_DIM + c];
+            }
+            s_a[r][c] = v;
+        }
+        __syncthreads();
+        Top2 st[MX_ROWS];
+#pragma unroll
+        for (int r = 0; r < MX_ROWS; ++r) st[r] = {INFINITY, -1, INFINITY};
+        const float* B = P.set_ptr[qb];
+        for (int jc = col0 + t; jc < col1; jc += 256) {
+            const float4* bp = reinterpret_cast<const float4*>(B + (size_t)jc * SFM_DESC_DIM);
+            float acc[MX_ROWS][8];
+            {
+                const float4 b0 = bp[0], b1 = bp[1];
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int r = 0; r < MX_ROWS; ++r)
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float tt = __fsub_rn(s_a[r][q], bb[q]);
+                        acc[r][q] = __fmul_rn(tt, tt);
+                    }
+            }
+#pragma unroll 1
+            for (int m = 1; m < 16; ++m) {
+                const float4 b0 = bp[2 * m], b1 = bp[2 * m + 1];
+                const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                for (int r = 0; r < MX_ROWS; ++r) {
+                    const float4 a0 = *reinterpret_cast<const float4*>(&s_a[r][8 * m]);
+                    const float4 a1 = *reinterpret_cast<const float4*>(&s_a[r][8 * m + 4]);
+                    const float aa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float tt = __fsub_rn(aa[q], bb[q]);
+                        acc[r][q] = __fadd_rn(acc[r][q], __fmul_rn(tt, tt));
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < MX_ROWS; ++r) {
+                float lo4 = __fadd_rn(__fadd_rn(acc[r][0], acc[r][1]), __fadd_rn(acc[r][2], acc[r][3]));
+                float hi4 = __fadd_rn(__fadd_rn(acc[r][4], acc[r][5]), __fadd_rn(acc[r][6], acc[r][7]));
+                top2_push(st[r], __fadd_rn(lo4, hi4), jc);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < MX_ROWS; ++r) {
+            Top2 v = st[r];
+            for (int o = 16; o > 0; o >>= 1) {
+                Top2 u;
+                u.d0 = __shfl_xor_sync(0xffffffffu, v.d0, o);
+                u.i0 = __shfl_xor_sync(0xffffffffu, v.i0, o);
+                u.d1 = __shfl_xor_sync(0xffffffffu, v.d1, o);
+                v = top2_merge(v, u);
+            }
+            if (lane == 0) s_red[warp][r] = v;
+        }
+        __syncthreads();
+        if (t < MX_ROWS) {
+            Top2 v = s_red[0][t];
+            for (int q = 1; q < 8; ++q) v = top2_merge(v, s_red[q][t]);
+            const int slot = rg * MX_ROWS + t;
+            if (slot < nflag)
+                P.part[((size_t)p * P.nmax + slot) * P.n_xchunks + ch] =
+                    make_float4(v.d0, __int_as_float(v.i0), v.d1, 0.f);
+        }
+    }
+}
+
+__global__ void k_match_merge(const __grid_constant__ MatchPlan P) {
+    const int p = blockIdx.y;
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= P.flag_cnt[p]) return;
+    const int n2 = P.set_cnt[P.pairs[2 * p + 1]];
+    const int nch = (n2 + MX_COLS - 1) / MX_COLS;
+    Top2 v = {INFINITY, -1, INFINITY};
+    for (int c = 0; c < nch; ++c) {
+        const float4 q = P.part[((size_t)p * P.nmax + slot) * P.n_xchunks + c];
+        Top2 u = {q.x, __float_as_int(q.y), q.z};
+        v = top2_merge(v, u);
+    }
+    const int row = P.flag_rows[(size_t)p * P.nmax + slot];
+    const size_t o = (size_t)p * P.nmax + row;
+    P.res_idx[o] = v.i0; P.res_d0[o] = v.d0; P.res_d1[o] = v.d1;
+}
+
+// ------------------------------------------------------------------ ratio test, ordering
+
+__global__ void k_match_emit(const __grid_constant__ MatchPlan P) {
+    const int p = blockIdx.y;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n1 = P.set_cnt[P.pairs[2 * p]], n2 = P.set_cnt[P.pairs[2 * p + 1]];
+    if (row >= n1 || n2 < 2) return;
+    const size_t o = (size_t)p * P.nmax + row;
+    const float d0 = __fsqrt_rn(P.res_d0[o]), d1 = __fsqrt_rn(P.res_d1[o]);   // :34
+    if (d1 > 0.0f) {                                                         // :46
+        const float nndr = __fdiv_rn(d0, d1);                                // :47
+        if (nndr <= P.thr) {                                                 // :49 (float32 compare)
+            const int pos = atomicAdd(&P.mcount[p], 1);
+            P.mkeys[(size_t)p * P.nmax + pos] =
+                ((unsigned long long)__float_as_uint(nndr) << 32) | (unsigned long long)(uint32_t)row;
+            P.midx[(size_t)p * P.nmax + pos] = P.res_idx[o];
+        }
+    }
+}
+
+// Rank sort by (confidence, query row): NNRatioFeatureMatcher.py:56-58 with the
+// tie order made canonical.
+__global__ void __launch_bounds__(256) k_match_sort(const __grid_constant__ MatchPlan P, int32_t* __restrict__ match_out,
+                                                    float* __restrict__ conf_out, int32_t* __restrict__ count_out,
+                                                    int32_t* __restrict__ stats_out) {
+    __shared__ unsigned long long s_k[256];
+    const int p = blockIdx.y;
+    const int n = P.mcount[p];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        count_out[p] = n < P.cap ? n : P.cap;
+        if (stats_out) { stats_out[2 * p] = P.flag_cnt[p]; stats_out[2 * p + 1] = P.stats[2 * p + 1]; }
+    }
+    if ((int)blockIdx.x * 256 >= n) return;
+    const unsigned long long* keys = P.mkeys + (size_t)p * P.nmax;
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    const unsigned long long mine = (e < n) ? keys[e] : 0ull;
+    int rank = 0;
+    for (int base = 0; base < n; base += 256) {
+        const int jx = base + threadIdx.x;
+        s_k[threadIdx.x] = (jx < n) ? keys[jx] : ~0ull;
+        __syncthreads();
+        if (e < n) {
+            const int m = min(256, n - base);
+            for (int q = 0; q < m; ++q) rank += (s_k[q] < mine) ? 1 : 0;
+        }
+        __syncthreads();
+    }
+    if (e >= n || rank >= P.cap) return;
+    const size_t o = (size_t)p * P.cap + rank;
+    match_out[2 * o] = (int32_t)(uint32_t)mine;
+    match_out[2 * o + 1] = P.midx[(size_t)p * P.nmax + e];
+    conf_out[o] = __uint_as_float((uint32_t)(mine >> 32));
+}
+
+// ------------------------------------------------------------------ host side
+
+static int choose_splits(int n_pairs, int nmax_pad) {
+    const int n_tiles = nmax_pad / MT_COLS;
+    const int rowblocks = nmax_pad / MT_ROWS;
+    const int min_s = (n_tiles + MT_MAX_TILES - 1) / MT_MAX_TILES;
+    const long long base = (long long)n_pairs * rowblocks;
+    const int sms = 148;                                   // B200
+    if (base >= 4LL * sms) return min_s;
+    int best = min_s;
+    double best_eff = -1.0;
+    for (int s = min_s; s <= MT_MAX_SPLITS && s <= n_tiles; ++s) {
+        const long long units = base * s;
+        const long long waves = (units + sms - 1) / sms;
+        double eff = (double)units / (double)(waves * sms);
+        // a split below 8 tiles pays too much prologue per unit
+        if ((n_tiles + s - 1) / s < 4 && s > min_s) break;
+        if (eff > best_eff + 0.02) { best_eff = eff; best = s; }
+    }
+    return best;
+}
+
+struct MatchWs {
+    size_t set_ptr, set_cnt, pairs, zero_begin, setmax, flag_cnt, mcount, stats, work_off, zero_end;
+    size_t h16, nb, hatn, resn, cands, res_idx, res_d0, res_d1, flag_rows, part, mkeys, midx, total;
+};
+
+static void match_layout(int n_sets, int nmax, int n_pairs, MatchPlan& P, MatchWs& ws) {
+    P.n_sets = n_sets; P.nmax = nmax; P.n_pairs = n_pairs;
+    P.nmax_pad = (int)align_up((size_t)std::max(nmax, 1), MT_ROWS);
+    P.n_tiles = P.nmax_pad / MT_COLS;
+    P.n_splits = choose_splits(n_pairs, P.nmax_pad);
+    P.tiles_per_split = (P.n_tiles + P.n_splits - 1) / P.n_splits;
+    P.n_lists = 2 * P.n_splits;
+    P.n_xchunks = (std::max(nmax, 1) + MX_COLS - 1) / MX_COLS;
+    const size_t rows = (size_t)n_sets * P.nmax_pad;
+    const size_t pr = (size_t)n_pairs * std::max(nmax, 1);
+    size_t o = 0;
+    auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
+    ws.set_ptr = take(sizeof(void*) * n_sets);
+    ws.set_cnt = take(sizeof(int32_t) * n_sets);
+    ws.pairs = take(sizeof(int32_t) * 2 * n_pairs);
+    ws.zero_begin = o;
+    ws.setmax = take(sizeof(float) * 4 * n_sets);
+    ws.flag_cnt = take(sizeof(int32_t) * n_pairs);
+    ws.mcount = take(sizeof(int32_t) * n_pairs);
+    ws.stats = take(sizeof(int32_t) * 2 * n_pairs);
+    ws.work_off = take(sizeof(int32_t) * (n_pairs + 1));
+    ws.zero_end = o;
+    ws.h16 = take(sizeof(__half) * rows * SFM_DESC_DIM);
+    ws.nb = take(sizeof(float) * rows);
+    ws.hatn = take(sizeof(float) * rows);
+    ws.resn = take(sizeof(float) * rows);
+    ws.cands = take(sizeof(uint32_t) * (size_t)n_pairs * P.nmax_pad * P.n_lists * MT_TOPK);
+    ws.res_idx = take(sizeof(int32_t) * pr);
+    ws.res_d0 = take(sizeof(float) * pr);
+    ws.res_d1 = take(sizeof(float) * pr);
+    ws.flag_rows = take(sizeof(int32_t) * pr);
+    ws.part = take(sizeof(float4) * pr * P.n_xchunks);
+    ws.mkeys = take(sizeof(unsigned long long) * pr);
+    ws.midx = take(sizeof(int32_t) * pr);
+    ws.total = o;
+}
+
+static void match_bind(MatchPlan& P, const MatchWs& ws, void* base) {
+    char* c = (char*)base;
+    P.set_ptr = (const float**)(c + ws.set_ptr);
+    P.set_cnt = (int32_t*)(c + ws.set_cnt);
+    P.pairs = (int32_t*)(c + ws.pairs);
+    P.setmax = (float*)(c + ws.setmax);
+    P.flag_cnt = (int32_t*)(c + ws.flag_cnt);
+    P.mcount = (int32_t*)(c + ws.mcount);
+    P.stats = (int32_t*)(c + ws.stats);
+    P.work_off = (int32_t*)(c + ws.work_off);
+    P.h16 = (__half*)(c + ws.h16);
+    P.nb = (float*)(c + ws.nb);
+    P.hatn = (float*)(c + ws.hatn);
+    P.resn = (float*)(c + ws.resn);
+    P.cands = (uint32_t*)(c + ws.cands);
+    P.res_idx = (int32_t*)(c + ws.res_idx);
+    P.res_d0 = (float*)(c + ws.res_d0);
+    P.res_d1 = (float*)(c + ws.res_d1);
+    P.flag_rows = (int32_t*)(c + ws.flag_rows);
+    P.part = (float4*)(c + ws.part);
+    P.mkeys = (unsigned long long*)(c + ws.mkeys);
+    P.midx = (int32_t*)(c + ws.midx);
+}
+
+static int run_match(SfmCtx* ctx, cudaStream_t st, MatchPlan& P, const MatchWs& ws, void* workspace,
+                     int32_t* match_out, float* conf_out, int32_t* count_out, int32_t* stats_out) {
+    SFM_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
+    SFM_CUDA_CHECK(ctx, cudaMemsetAsync((char*)workspace + ws.zero_begin, 0, ws.zero_end - ws.zero_begin, st));
+    const int nt = std::max(P.n_sets, P.n_pairs);
+    k_match_setup<<<ceil_div(nt, 256), 256, 0, st>>>(P);
+    SFM_LAUNCH_CHECK(ctx, "k_match_setup");
+    const dim3 rowgrid(ceil_div(P.nmax, 256), P.n_pairs);
+    if (P.mode == SFM_MATCH_AUTO) {
+        k_match_prep<<<dim3(P.nmax_pad / 8, P.n_sets), 256, 0, st>>>(P);
+        SFM_LAUNCH_CHECK(ctx, "k_match_prep");
+        int rc = launch_match_tc(ctx, st, P);
+        if (rc) return rc;
+        k_match_recheck<<<dim3(ceil_div(P.nmax, 8), P.n_pairs), 256, 0, st>>>(P);
+        SFM_LAUNCH_CHECK(ctx, "k_match_recheck");
+    } else {
+        k_flag_all<<<rowgrid, 256, 0, st>>>(P);
+        SFM_LAUNCH_CHECK(ctx, "k_flag_all");
+    }
+    k_work_scan<<<1, 32, 0, st>>>(P);
+    SFM_LAUNCH_CHECK(ctx, "k_work_scan");
+    k_match_exact<<<2 * ctx->sm_count, 256, 0, st>>>(P);
+    SFM_LAUNCH_CHECK(ctx, "k_match_exact");
+    k_match_merge<<<rowgrid, 256, 0, st>>>(P);
+    SFM_LAUNCH_CHECK(ctx, "k_match_merge");
+    k_match_emit<<<rowgrid, 256, 0, st>>>(P);
+    SFM_LAUNCH_CHECK(ctx, "k_match_emit");
+    k_match_sort<<<rowgrid, 256, 0, st>>>(P, match_out, conf_out, count_out, stats_out);
+    SFM_LAUNCH_CHECK(ctx, "k_match_sort");
+    return SFM_OK;
+}
+
+extern "C" {
+
+size_t sfm_match_workspace_bytes(int n_sets, int nmax, int n_pairs) {
+    if (n_sets < 1 || nmax < 1 || n_pairs < 1) return 0;
+    MatchPlan P;
+    MatchWs ws;
+    memset(&P, 0, sizeof(P));
+    match_layout(n_sets, nmax, n_pairs, P, ws);
+    return ws.total;
+}
+
+int sfm_match_ratio(SfmCtx* ctx, void* stream, const float* f1_dev, int n1, const float* f2_dev,
+                    int n2, int dim, float ratio_threshold, int mode, void* workspace_dev,
+                    size_t workspace_bytes, int32_t* match_out, float* conf_out,
+                    int32_t* count_out, int cap) {
+    if (!ctx) return SFM_ERR_BAD_ARG;
+    if (dim != SFM_DESC_DIM) return sfm_set_error(ctx, SFM_ERR_UNSUPPORTED, "descriptor dim %d != 128", dim);
+    if (!f1_dev || !f2_dev || !workspace_dev || !match_out || !conf_out || !count_out)
+        return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "NULL pointer");
+    if (n1 < 1 || n2 < 2)
+        return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "need n1 >= 1 and n2 >= 2 (got %d, %d): the reference indexes the second neighbour", n1, n2);
+    if (((uintptr_t)f1_dev | (uintptr_t)f2_dev) & 15)
+        return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "descriptor pointers must be 16-byte aligned");
+    if (mode != SFM_MATCH_AUTO && mode != SFM_MATCH_EXACT) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "bad mode");
+    MatchPlan P;
+    MatchWs ws;
+    memset(&P, 0, sizeof(P));
+    match_layout(2, std::max(n1, n2), 1, P, ws);
+    if (workspace_bytes < ws.total)
+        return sfm_set_error(ctx, SFM_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, ws.total);
+    if (cap < 1) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "cap < 1");
+    match_bind(P, ws, workspace_dev);
+    P.f1 = f1_dev; P.f2 = f2_dev; P.n1 = n1; P.n2 = n2;
+    P.thr = ratio_threshold; P.mode = mode; P.cap = cap;
+    return run_match(ctx, (cudaStream_t)stream, P, ws, workspace_dev, match_out, conf_out, count_out, nullptr);
+}
+
+int sfm_match_ratio_batch(SfmCtx* ctx, void* stream, const float* desc_dev, const int32_t* counts_dev,
+                          int n_sets, int nmax, const int32_t* pairs_dev, int n_pairs,
+                          float ratio_threshold, int mode, void* workspace_dev, size_t workspace_bytes,
+                          int32_t* match_out, float* conf_out, int32_t* count_out, int32_t* stats_out,
+                          int cap) {
+    if (!ctx) return SFM_ERR_BAD_ARG;
+    if (!desc_dev || !counts_dev || !pairs_dev || !workspace_dev || !match_out || !conf_out || !count_out)
+        return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "NULL pointer");
+    if (n_sets < 1 || nmax < 2 || n_pairs < 1) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "bad sizes");
+    if ((uintptr_t)desc_dev & 15) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "descriptor pointer must be 16-byte aligned");
+    if (mode != SFM_MATCH_AUTO && mode != SFM_MATCH_EXACT) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "bad mode");
+    MatchPlan P;
+    MatchWs ws;
+    memset(&P, 0, sizeof(P));
+    match_layout(n_sets, nmax, n_pairs, P, ws);
+    if (workspace_bytes < ws.total)
+        return sfm_set_error(ctx, SFM_ERR_WORKSPACE, "workspace %zu < required %zu", workspace_bytes, ws.total);
+    if (cap < 1) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "cap < 1");
+    match_bind(P, ws, workspace_dev);
+    P.desc = desc_dev; P.counts_in = counts_dev; P.pairs_in = pairs_dev;
+    P.thr = ratio_threshold; P.mode = mode; P.cap = cap;
+    return run_match(ctx, (cudaStream_t)stream, P, ws, workspace_dev, match_out, conf_out, count_out, stats_out);
+}
+
+}  // extern "C"
