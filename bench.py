@@ -1,0 +1,381 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the SfmFromScratch feature hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" is one pass of the hot path over one batch per GPU: SIFT extraction
+(ScaleRotInvSIFT, reference defaults) of 32 synthetic 1920x1080 images
+(BASELINE.json configs[1] image shape, configs[3]'s per-GPU share at 8 GPUs),
+the all-gather of the descriptor blocks when N > 1, and NN-ratio matching of
+this rank's share of the consecutive image pairs (what Runner.py:183-191
+matches).  `value` is input Mpixel/s of the whole job with the images resident
+in HBM; `e2e` repeats the step through host buffers (pinned H2D of the images,
+D2H of keypoints, descriptors and matches inside the timed region).  The
+matcher is also measured alone on configs[4]-shaped pairs (8192 x 8192
+descriptors) and reported under "match" with its tensor-pipe roofline.
+
+The reference arm (--impl reference) times the CPU oracle port of the same
+path (the reference is pure Python and cannot travel to the GPU box; see
+DESIGN.md) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+IMG_H, IMG_W, BATCH = 1080, 1920, 32
+N_DISTINCT = 8                  # distinct synthetic images, tiled to the batch
+MATCH_SETS, MATCH_N = 12, 8192  # matcher-only leg: all 66 pairs of 12 sets of 8192 descriptors
+RATIO = 0.8
+METRIC = "sift_extract_plus_nn_ratio_match_input_mpixel_per_s"
+WORKLOAD = (f"ScaleRotInvSIFT(defaults: 4 levels, k=2500) on {BATCH} synthetic {IMG_W}x{IMG_H} f32 images per GPU "
+            f"(configs[1] image, configs[3] per-GPU share) + NN-ratio matching (thr {RATIO}) of consecutive image pairs")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def level_pixels(h, w, levels=4, f=2):
+    tot = 0
+    for _ in range(levels):
+        tot += h * w
+        h, w = int(h / f), int(w / f)
+    return tot
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {getattr(nv, k): k for k in dir(nv) if k.startswith("nvmlClocksEventReason") or k.startswith("nvmlClocksThrottleReason")}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, nm in names.items():
+                    if isinstance(bit, int) and bit and (r & bit) and "None" not in nm and "All" not in nm:
+                        self.reasons.add(nm.replace("nvmlClocksEventReason", "").replace("nvmlClocksThrottleReason", ""))
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------- CPU arm (oracle port)
+
+def _cpu_init():
+    from oracle import oracle as O
+    O.lib()
+
+
+def _cpu_extract(img):
+    from oracle import oracle as O
+    e = O.ScaleRotInvSIFT(img, {})
+    return e.extract_descriptors()
+
+
+def _cpu_match(args):
+    from oracle import oracle as O
+    f1, f2 = args
+    return len(O.NNRatioFeatureMatcher(RATIO).match_features_ratio_test(f1, f2)[0])
+
+
+def cpu_images(n_images):
+    from sfmfromscratch_b200.synth import synth_image
+    return [synth_image(IMG_H, IMG_W, s) for s in range(n_images)]
+
+
+def cpu_sample(images, pool=None):
+    """The oracle port on `images` (1080p) + their consecutive-pair matches, in
+    this process or over `pool`; returns (Mpixel/s, seconds).  Input synthesis
+    and worker start-up are outside the timed region."""
+    n = len(images)
+    t0 = time.time()
+    if pool is None:
+        feats = [_cpu_extract(im) for im in images]
+        for i in range(n - 1):
+            _cpu_match((feats[i], feats[i + 1]))
+    else:
+        feats = pool.map(_cpu_extract, images, chunksize=1)
+        pool.map(_cpu_match, [(feats[i], feats[i + 1]) for i in range(n - 1)], chunksize=1)
+    dt = time.time() - t0
+    return n * IMG_H * IMG_W / dt / 1e6, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    n = max(cores, 2)
+    images = cpu_images(n)
+    steps = max(1, min(args.steps, 3))          # bounded: each step is a sample of the workload
+    vals, times = [], []
+    with mp.get_context("spawn").Pool(cores, initializer=_cpu_init) as pool:
+        pool.map(_cpu_extract, images[:cores], chunksize=1)     # warm-up: imports, page-in
+        for _ in range(steps):
+            v, dt = cpu_sample(images, pool)
+            vals.append(v); times.append(dt)
+    value = float(np.mean(vals))
+    sample = (f"each step = {n} of the workload's {BATCH} 1080p images + their {n - 1} consecutive-pair matches, "
+              f"oracle port (C + numpy restatement of the reference; the reference itself is pure Python and is not on this box), "
+              f"{cores} worker processes; {steps} steps timed")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": args.gpus,
+            "steps": steps, "warmup": 1, "ms_per_step": float(np.mean(times)) * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": value, "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------- GPU arm
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sfmfromscratch_b200 import _native as N
+    from sfmfromscratch_b200 import pipeline as PL
+    from sfmfromscratch_b200.extractor import extract_batch_device, make_params
+    from sfmfromscratch_b200.matcher import match_batch_device
+    from sfmfromscratch_b200.synth import synth_descriptor_base, synth_descriptors, synth_image
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N.load_library()
+    N.get_ctx(local)
+    pk = peaks()
+
+    # ---- inputs (synthetic, seeded; different per rank)
+    base_imgs = np.stack([synth_image(IMG_H, IMG_W, 1000 * rank + s) for s in range(N_DISTINCT)])
+    host_batch = torch.from_numpy(np.concatenate([base_imgs] * (BATCH // N_DISTINCT))).pin_memory()
+    images = host_batch.to(dev)
+    params, keep = make_params({}, pyramid=True)
+    pairs_global = PL.consecutive_pairs(world * BATCH)
+    my_pairs_np = PL.deal_pairs(pairs_global, rank, world, block=4)
+    my_pairs = torch.from_numpy(np.ascontiguousarray(my_pairs_np)).to(dev)
+    n_my_pairs = int(my_pairs.shape[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(imgs):
+        out = extract_batch_device(imgs, params, want_aux=False)
+        d_all, c_all = PL.gather_descriptors(out['desc'], out['count'])
+        m = match_batch_device(d_all, c_all, my_pairs, RATIO, cap=2500) if n_my_pairs else None
+        return out, m
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            fn()
+        b.record()
+        barrier()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- main timed region (resident inputs), per-kernel events + clock sampling live
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        step(images)
+    barrier()
+    N.profile_enable(True, local)
+    l0 = N.launch_count(local)
+    sampler.start()
+    total_ms = timed(lambda: step(images), args.steps, 0)
+    sampler.stop_flag = True
+    launches = N.launch_count(local) - l0
+    kstat = N.profile_collect(local)
+    N.profile_enable(False, local)
+    sampler.join(timeout=2)
+    ms_per_step = total_ms / args.steps
+    pixels_per_step = world * BATCH * IMG_H * IMG_W
+    value = pixels_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # unprofiled repeat: the event pairs must not have distorted the number
+    plain_ms = timed(lambda: step(images), args.steps, 0) / args.steps
+
+    # ---- roofline of the dominant kernel (k_harris): 4 B read + 4 B written per pyramid pixel
+    lp = level_pixels(IMG_H, IMG_W)
+    kh = kstat.get("k_harris", (0, 0.0))
+    kh_ms_step = kh[1] / args.steps if kh[1] else float("nan")
+    harris_bytes = 8.0 * lp * BATCH
+    achieved = harris_bytes / (kh_ms_step * 1e-3) / 1e9 if kh[1] else None
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("k_harris_dram_bytes_per_step")
+    roofline = {"kernel": "k_harris (fused Sobel + second moments + 7x7 window + R)", "bound": "hbm",
+                "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": (achieved / pk["hbm"]) if achieved else None,
+                "traffic": traffic, "peak_source": pk["src"],
+                "algorithmic_bytes_per_step": harris_bytes, "kernel_ms_per_step": kh_ms_step,
+                "share_of_step": (kh_ms_step / ms_per_step) if kh[1] else None,
+                "note": "per-kernel CUDA events on the launching stream, recorded inside the timed region; the 147-FMA "
+                        "bit-exact window chain makes this kernel FP32-issue bound, see DESIGN.md"}
+    kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in sorted(kstat.items())}
+
+    # ---- e2e: host buffers in and out, copies inside the timed region
+    cap = 2500
+    h_x = torch.empty((BATCH, cap), dtype=torch.int32).pin_memory()
+    h_y = torch.empty((BATCH, cap), dtype=torch.int32).pin_memory()
+    h_d = torch.empty((BATCH, cap, 128), dtype=torch.float32).pin_memory()
+    h_c = torch.empty((BATCH,), dtype=torch.int32).pin_memory()
+    h_m = torch.empty((max(n_my_pairs, 1), cap, 2), dtype=torch.int32).pin_memory()
+    h_mc = torch.empty((max(n_my_pairs, 1), cap), dtype=torch.float32).pin_memory()
+    h_mn = torch.empty((max(n_my_pairs, 1),), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        imgs = host_batch.to(dev, non_blocking=True)
+        out, m = step(imgs)
+        h_x.copy_(out['x'], non_blocking=True); h_y.copy_(out['y'], non_blocking=True)
+        h_d.copy_(out['desc'], non_blocking=True); h_c.copy_(out['count'], non_blocking=True)
+        if m is not None:
+            h_m.copy_(m[0], non_blocking=True); h_mc.copy_(m[1], non_blocking=True); h_mn.copy_(m[2], non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 30))
+    e2e_ms = timed(e2e_step, e2e_steps, min(args.warmup, 3)) / e2e_steps
+    h2d = host_batch.numel() * 4
+    d2h = (h_x.numel() + h_y.numel() + h_d.numel() + h_c.numel()) * 4
+    if n_my_pairs:
+        d2h += (h_m.numel() + h_mc.numel() + h_mn.numel()) * 4
+    e2e = {"value": pixels_per_step / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "extract_batch_device + match_batch_device behind pinned torch copies (the calls ScaleRotInvSIFT / "
+                  "NNRatioFeatureMatcher make)"}
+
+    # ---- matcher alone on configs[4]-shaped pairs
+    base = synth_descriptor_base(MATCH_N)
+    sets = np.stack([synth_descriptors(MATCH_N, 100 * rank + i, base=base) for i in range(MATCH_SETS)])
+    d_sets = torch.from_numpy(sets).to(dev)
+    d_cnt = torch.full((MATCH_SETS,), MATCH_N, dtype=torch.int32, device=dev)
+    d_pairs = torch.from_numpy(PL.all_pairs(MATCH_SETS)).to(dev)
+    n_mp = int(d_pairs.shape[0])
+    msteps = max(3, min(args.steps, 20))
+    for _ in range(3):
+        match_batch_device(d_sets, d_cnt, d_pairs, RATIO, cap=MATCH_N)
+    barrier()
+    N.profile_enable(True, local)
+    m_ms = timed(lambda: match_batch_device(d_sets, d_cnt, d_pairs, RATIO, cap=MATCH_N), msteps, 0) / msteps
+    mstat = N.profile_collect(local)
+    N.profile_enable(False, local)
+    mm, mc, mcnt, mst = match_batch_device(d_sets, d_cnt, d_pairs, RATIO, cap=MATCH_N, want_stats=True)
+    torch.cuda.synchronize()
+    dpairs = float(n_mp) * MATCH_N * MATCH_N
+    tc = mstat.get("k_match_tc", (0, 0.0))
+    tc_ms = tc[1] / msteps if tc[1] else float("nan")
+    tc_ach = 256.0 * dpairs / (tc_ms * 1e-3) / 1e12 if tc[1] else None
+    match = {"metric": "nn_ratio_descriptor_pairs_per_s", "value": world * dpairs / (m_ms * 1e-3), "unit": "descriptor-pairs/s",
+             "image_pairs_per_s": world * n_mp / (m_ms * 1e-3), "ms_per_step": m_ms, "steps": msteps,
+             "workload": f"all {n_mp} pairs of {MATCH_SETS} sets of {MATCH_N} x 128 f32 descriptors per GPU (configs[4] pair shape), thr {RATIO}",
+             "matches_per_pair_mean": float(mcnt.float().mean().item()),
+             "rows_rescanned_exact_frac": float(mst[:, 0].float().sum().item()) / (n_mp * MATCH_N),
+             "candidate_groups_rechecked_per_row": float(mst[:, 1].float().sum().item()) / (n_mp * MATCH_N),
+             "kernels": {k: {"launches_per_step": v[0] / msteps, "ms_per_step": v[1] / msteps} for k, v in sorted(mstat.items())},
+             "roofline": {"kernel": "k_match_tc (tcgen05 fp16 GEMM + fused top-4 epilogue)", "bound": "tensor",
+                          "achieved": tc_ach, "peak": pk["tf_sust"], "unit": "TFLOP/s",
+                          "frac": (tc_ach / pk["tf_sust"]) if tc_ach else None, "traffic": None,
+                          "peak_source": pk["src"] + ", sustained bf16 (fp16 runs at the same rate)",
+                          "flops": "256 per descriptor pair (algorithmic == executed: single fp16 pass)"}}
+
+    # ---- CPU baseline on a bounded sample (rank 0, N == 1 only)
+    cpu = None
+    if world == 1 and rank == 0 and not args.no_cpu:
+        n_cpu = 8
+        v, dt = cpu_sample(cpu_images(n_cpu))
+        cpu = {"value": v, "unit": "Mpixel/s", "cores": 1, "kind": "port", "seconds": dt,
+               "sample": f"{n_cpu} of the step's {BATCH} 1080p images + their {n_cpu - 1} consecutive-pair matches through the "
+                         f"CPU oracle (C + numpy port of the reference), one process; the reference's own Python loops are ~15x "
+                         f"slower per image (BASELINE.md section 2)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "images_per_gpu": BATCH, "image": [IMG_H, IMG_W],
+                           "distinct_images": N_DISTINCT, "pairs_per_gpu": n_my_pairs,
+                           "l2": "inputs larger than L2 (265 MB of images, 352 MB of R planes per step)",
+                           "parallelism": f"image shards x{world}, descriptor all-gather (NCCL), pair shards"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+                "clocks": sampler.summary(), "ms_per_step_unprofiled": plain_ms, "kernels": kernels, "match": match}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    del keep
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,21 @@ SFM_EXPORT const char* sfm_last_error(SfmCtx* ctx);
 /* Number of SMs of the context's device (grid sizing for callers/tests). */
 SFM_EXPORT int  sfm_ctx_sm_count(SfmCtx* ctx);
 
+/* Kernel launches issued through this context so far (bench.py's gpu_launches). */
+SFM_EXPORT unsigned long long sfm_ctx_launch_count(SfmCtx* ctx);
+
+/* Optional per-kernel timing: while enabled, every kernel the library launches
+ * is bracketed by two CUDA events on the launching stream.  sfm_profile_collect
+ * waits for the recorded events, aggregates them by kernel name into out[0..cap)
+ * and returns the number of distinct kernels (records are consumed). */
+typedef struct SfmKernelStat {
+    char    name[48];
+    int32_t launches;
+    float   total_ms;
+} SfmKernelStat;
+SFM_EXPORT int sfm_profile_enable(SfmCtx* ctx, int on);
+SFM_EXPORT int sfm_profile_collect(SfmCtx* ctx, SfmKernelStat* out, int cap);
+
 /* Fill p with the reference defaults. */
 SFM_EXPORT void sfm_extract_default_params(SfmExtractParams* p);
 

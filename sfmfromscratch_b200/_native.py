@@ -25,6 +25,7 @@ DESC_DIM = 128
 # every symbol include/sfmb200.h declares
 EXPORTS = [
     "sfm_version", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_error", "sfm_ctx_sm_count",
+    "sfm_ctx_launch_count", "sfm_profile_enable", "sfm_profile_collect",
     "sfm_extract_default_params", "sfm_extract_max_keypoints", "sfm_extract_workspace_bytes",
     "sfm_extract_batch", "sfm_extract_status", "sfm_harris_response",
     "sfm_match_workspace_bytes", "sfm_match_ratio", "sfm_match_ratio_batch",
@@ -46,6 +47,10 @@ class SfmExtractParams(C.Structure):
         ("cand_full", C.c_int32),
         ("gauss_weights", C.POINTER(C.c_float)),
     ]
+
+
+class SfmKernelStat(C.Structure):
+    _fields_ = [("name", C.c_char * 48), ("launches", C.c_int32), ("total_ms", C.c_float)]
 
 
 _lib = None
@@ -73,6 +78,10 @@ def load_library() -> C.CDLL:
         L.sfm_last_error.argtypes = [C.c_void_p]
         L.sfm_last_error.restype = C.c_char_p
         L.sfm_ctx_sm_count.argtypes = [C.c_void_p]
+        L.sfm_ctx_launch_count.argtypes = [C.c_void_p]
+        L.sfm_ctx_launch_count.restype = C.c_ulonglong
+        L.sfm_profile_enable.argtypes = [C.c_void_p, C.c_int]
+        L.sfm_profile_collect.argtypes = [C.c_void_p, C.POINTER(SfmKernelStat), C.c_int]
         L.sfm_extract_default_params.argtypes = [PP]
         L.sfm_extract_default_params.restype = None
         L.sfm_extract_max_keypoints.argtypes = [PP]
@@ -116,3 +125,20 @@ def get_ctx(device: int = 0) -> int:
 def check(rc: int, ctx: int) -> None:
     if rc != SFM_OK:
         raise SfmError(rc, load_library().sfm_last_error(ctx).decode())
+
+
+def launch_count(device: int = 0) -> int:
+    return int(load_library().sfm_ctx_launch_count(get_ctx(device)))
+
+
+def profile_enable(on: bool, device: int = 0) -> None:
+    check(load_library().sfm_profile_enable(get_ctx(device), 1 if on else 0), get_ctx(device))
+
+
+def profile_collect(device: int = 0) -> dict:
+    """{kernel name: (launches, total_ms)} of the launches recorded since the last call."""
+    arr = (SfmKernelStat * 64)()
+    n = load_library().sfm_profile_collect(get_ctx(device), arr, 64)
+    if n < 0:
+        check(n, get_ctx(device))
+    return {arr[i].name.decode(): (int(arr[i].launches), float(arr[i].total_ms)) for i in range(n)}

@@ -1,5 +1,29 @@
 // api.cu -- context management for libsfmb200 (C ABI in include/sfmb200.h).
+#include <cstring>
+
 #include "common.cuh"
+
+// Per-launch accounting.  With profiling off this is one atomic increment; with
+// it on every launch is bracketed by two CUDA events on the launching stream.
+int sfm_prof_begin(SfmCtx* ctx, cudaStream_t st, const char* name) {
+    ctx->launches.fetch_add(1);
+    if (!ctx->prof_on) return -1;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; ++i) {
+        if (!ctx->ev_pool.empty()) { ev[i] = ctx->ev_pool.back(); ctx->ev_pool.pop_back(); }
+        else if (cudaEventCreate(&ev[i]) != cudaSuccess) return -1;
+    }
+    cudaEventRecord(ev[0], st);
+    ctx->prof.push_back({name, ev[0], ev[1]});
+    return (int)ctx->prof.size() - 1;
+}
+
+void sfm_prof_end(SfmCtx* ctx, cudaStream_t st, int idx) {
+    if (idx < 0) return;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    if (idx < (int)ctx->prof.size()) cudaEventRecord(ctx->prof[idx].b, st);
+}
 
 extern "C" {
 
@@ -36,7 +60,12 @@ int sfm_ctx_create(int device, SfmCtx** out) {
     return SFM_OK;
 }
 
-void sfm_ctx_destroy(SfmCtx* ctx) { delete ctx; }
+void sfm_ctx_destroy(SfmCtx* ctx) {
+    if (!ctx) return;
+    for (auto& r : ctx->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    for (auto e : ctx->ev_pool) cudaEventDestroy(e);
+    delete ctx;
+}
 
 const char* sfm_last_error(SfmCtx* ctx) {
     if (!ctx) return g_noctx_err.c_str();
@@ -48,5 +77,40 @@ const char* sfm_last_error(SfmCtx* ctx) {
 }
 
 int sfm_ctx_sm_count(SfmCtx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+unsigned long long sfm_ctx_launch_count(SfmCtx* ctx) { return ctx ? ctx->launches.load() : 0ull; }
+
+int sfm_profile_enable(SfmCtx* ctx, int on) {
+    if (!ctx) return SFM_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    for (auto& r : ctx->prof) { ctx->ev_pool.push_back(r.a); ctx->ev_pool.push_back(r.b); }
+    ctx->prof.clear();
+    ctx->prof_on = on != 0;
+    return SFM_OK;
+}
+
+int sfm_profile_collect(SfmCtx* ctx, SfmKernelStat* out, int cap) {
+    if (!ctx || (!out && cap > 0)) return SFM_ERR_BAD_ARG;
+    std::lock_guard<std::mutex> g(ctx->mu);
+    int n = 0;
+    for (auto& r : ctx->prof) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) ms = 0.f;
+        int k = 0;
+        for (; k < n; ++k) if (strncmp(out[k].name, r.name, sizeof(out[k].name) - 1) == 0) break;
+        if (k == n) {
+            if (n >= cap) continue;
+            memset(&out[n], 0, sizeof(SfmKernelStat));
+            strncpy(out[n].name, r.name, sizeof(out[n].name) - 1);
+            ++n;
+        }
+        out[k].launches += 1;
+        out[k].total_ms += ms;
+        ctx->ev_pool.push_back(r.a);
+        ctx->ev_pool.push_back(r.b);
+    }
+    ctx->prof.clear();
+    return n;
+}
 
 }  // extern "C"

@@ -3,8 +3,10 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <atomic>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/sfmb200.h"
 
@@ -16,7 +18,25 @@ struct SfmCtx {
     std::mutex mu;
     std::string err;
     void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled, resolved lazily
+    // launch accounting / optional per-kernel CUDA-event timing (sfm_profile_*)
+    std::atomic<unsigned long long> launches{0};
+    bool prof_on = false;
+    struct ProfRec { const char* name; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> ev_pool;
 };
+
+int sfm_prof_begin(SfmCtx* ctx, cudaStream_t st, const char* name);
+void sfm_prof_end(SfmCtx* ctx, cudaStream_t st, int idx);
+
+// Launch a kernel with accounting: SFM_LAUNCH(ctx, stream, "name", kernel<<<g, b, s, stream>>>(args));
+#define SFM_LAUNCH(ctx, st, name, ...)                                                    \
+    do {                                                                                  \
+        int _pi = sfm_prof_begin((ctx), (st), (name));                                    \
+        __VA_ARGS__;                                                                      \
+        sfm_prof_end((ctx), (st), _pi);                                                   \
+        SFM_LAUNCH_CHECK((ctx), (name));                                                  \
+    } while (0)
 
 int sfm_set_error(SfmCtx* ctx, int code, const char* fmt, ...);
 

@@ -505,30 +505,21 @@ static int run_match(SfmCtx* ctx, cudaStream_t st, MatchPlan& P, const MatchWs& 
     SFM_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     SFM_CUDA_CHECK(ctx, cudaMemsetAsync((char*)workspace + ws.zero_begin, 0, ws.zero_end - ws.zero_begin, st));
     const int nt = std::max(P.n_sets, P.n_pairs);
-    k_match_setup<<<ceil_div(nt, 256), 256, 0, st>>>(P);
-    SFM_LAUNCH_CHECK(ctx, "k_match_setup");
+    SFM_LAUNCH(ctx, st, "k_match_setup", k_match_setup<<<ceil_div(nt, 256), 256, 0, st>>>(P));
     const dim3 rowgrid(ceil_div(P.nmax, 256), P.n_pairs);
     if (P.mode == SFM_MATCH_AUTO) {
-        k_match_prep<<<dim3(P.nmax_pad / 8, P.n_sets), 256, 0, st>>>(P);
-        SFM_LAUNCH_CHECK(ctx, "k_match_prep");
+        SFM_LAUNCH(ctx, st, "k_match_prep", k_match_prep<<<dim3(P.nmax_pad / 8, P.n_sets), 256, 0, st>>>(P));
         int rc = launch_match_tc(ctx, st, P);
         if (rc) return rc;
-        k_match_recheck<<<dim3(ceil_div(P.nmax, 8), P.n_pairs), 256, 0, st>>>(P);
-        SFM_LAUNCH_CHECK(ctx, "k_match_recheck");
+        SFM_LAUNCH(ctx, st, "k_match_recheck", k_match_recheck<<<dim3(ceil_div(P.nmax, 8), P.n_pairs), 256, 0, st>>>(P));
     } else {
-        k_flag_all<<<rowgrid, 256, 0, st>>>(P);
-        SFM_LAUNCH_CHECK(ctx, "k_flag_all");
+        SFM_LAUNCH(ctx, st, "k_flag_all", k_flag_all<<<rowgrid, 256, 0, st>>>(P));
     }
-    k_work_scan<<<1, 32, 0, st>>>(P);
-    SFM_LAUNCH_CHECK(ctx, "k_work_scan");
-    k_match_exact<<<2 * ctx->sm_count, 256, 0, st>>>(P);
-    SFM_LAUNCH_CHECK(ctx, "k_match_exact");
-    k_match_merge<<<rowgrid, 256, 0, st>>>(P);
-    SFM_LAUNCH_CHECK(ctx, "k_match_merge");
-    k_match_emit<<<rowgrid, 256, 0, st>>>(P);
-    SFM_LAUNCH_CHECK(ctx, "k_match_emit");
-    k_match_sort<<<rowgrid, 256, 0, st>>>(P, match_out, conf_out, count_out, stats_out);
-    SFM_LAUNCH_CHECK(ctx, "k_match_sort");
+    SFM_LAUNCH(ctx, st, "k_work_scan", k_work_scan<<<1, 32, 0, st>>>(P));
+    SFM_LAUNCH(ctx, st, "k_match_exact", k_match_exact<<<2 * ctx->sm_count, 256, 0, st>>>(P));
+    SFM_LAUNCH(ctx, st, "k_match_merge", k_match_merge<<<rowgrid, 256, 0, st>>>(P));
+    SFM_LAUNCH(ctx, st, "k_match_emit", k_match_emit<<<rowgrid, 256, 0, st>>>(P));
+    SFM_LAUNCH(ctx, st, "k_match_sort", k_match_sort<<<rowgrid, 256, 0, st>>>(P, match_out, conf_out, count_out, stats_out));
     return SFM_OK;
 }
 

@@ -339,7 +339,6 @@ int launch_match_tc(SfmCtx* ctx, cudaStream_t st, const MatchPlan& P) {
     const int n_units = P.n_pairs * (P.nmax_pad / MT_ROWS) * P.n_splits;
     SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     const int grid = n_units < ctx->sm_count ? n_units : ctx->sm_count;
-    k_match_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(P, tmap, n_units);
-    SFM_LAUNCH_CHECK(ctx, "k_match_tc");
+    SFM_LAUNCH(ctx, st, "k_match_tc", k_match_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(P, tmap, n_units));
     return SFM_OK;
 }

@@ -222,3 +222,17 @@ def extract_batch(images, extractor_params: Optional[dict] = None, *, pyramid: b
     x, y, d = out['x'].cpu().numpy(), out['y'].cpu().numpy(), out['desc'].cpu().numpy()
     del keep
     return [(x[b, :n].astype(np.int64), y[b, :n].astype(np.int64), d[b, :n]) for b, n in enumerate(counts)]
+
+
+def harris_response(image: np.ndarray, extractor_params: Optional[dict] = None) -> np.ndarray:
+    """R map of NaiveSIFT.py:60-74 through sfm_harris_response (parity tests)."""
+    p, keep = make_params(extractor_params, pyramid=False)
+    img = _to_device(image)
+    H, W = img.shape
+    out = torch.empty((H, W), dtype=torch.float32, device=img.device)
+    L = N.load_library()
+    ctx = N.get_ctx(img.device.index)
+    N.check(L.sfm_harris_response(ctx, _stream_ptr(), img.data_ptr(), H, W, C.byref(p), out.data_ptr()), ctx)
+    res = out.cpu().numpy()
+    del keep
+    return res

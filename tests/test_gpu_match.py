@@ -1,0 +1,138 @@
+"""Parity of the CUDA matcher (through the C ABI) with the oracle / reference
+goldens.  Needs a B200: pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from parity import assert_matches_identical  # noqa: E402
+
+AUTO, EXACT = 0, 1
+
+
+def _mods():
+    from oracle import oracle as O
+    import sfmfromscratch_b200 as S
+    return O, S
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("mode", [AUTO, EXACT])
+def test_matcher_golden(golden_dir, mode):
+    """Reference outputs incl. duplicate train rows, an exact hit (d0 == 0) and a zero descriptor."""
+    _, S = _mods()
+    g = load(golden_dir, "matcher_220x260.npz")
+    for thr, mk, ck in ((0.8, "matches", "conf"), (0.95, "matches95", "conf95")):
+        m, c = S.NNRatioFeatureMatcher(thr, mode=mode).match_features_ratio_test(g["f1"], g["f2"])
+        assert m.dtype == np.int64 and c.dtype == np.float32 and m.shape[1] == 2
+        assert_matches_identical(m, c, g[mk], g[ck])
+
+
+@pytest.mark.parametrize("mode", [AUTO, EXACT])
+def test_two_view_golden_descriptors(golden_dir, mode):
+    """The reference's own descriptors of the two-view pair -> the reference's matches, bit for bit."""
+    _, S = _mods()
+    for name in ("two_view_96x128.npz", "two_view_240x320.npz"):
+        g = load(golden_dir, name)
+        m, c = S.NNRatioFeatureMatcher(0.8, mode=mode).match_features_ratio_test(g["D1"], g["D2"])
+        assert_matches_identical(m, c, g["matches"], g["conf"])
+
+
+@pytest.mark.parametrize("n1,n2,thr", [(1, 2, 0.9), (3, 2, 0.9), (5, 300, 0.8), (300, 5, 0.8), (129, 257, 0.7),
+                                        (1000, 1100, 0.8), (2048, 2300, 0.85), (4097, 1025, 0.8), (700, 9000, 0.8)])
+@pytest.mark.parametrize("mode", [AUTO, EXACT])
+def test_matcher_vs_oracle(n1, n2, thr, mode):
+    O, S = _mods()
+    from sfmfromscratch_b200.synth import synth_descriptors
+    base_n = max(n1, n2)
+    from sfmfromscratch_b200.synth import synth_descriptor_base
+    base = synth_descriptor_base(base_n)
+    f1 = synth_descriptors(n1, n1, base=base)
+    f2 = synth_descriptors(n2, n2 + 1, base=base)
+    m, c = S.NNRatioFeatureMatcher(thr, mode=mode).match_features_ratio_test(f1, f2)
+    mo, co = O.NNRatioFeatureMatcher(thr).match_features_ratio_test(f1, f2)
+    assert_matches_identical(m, c, mo, co)
+
+
+@pytest.mark.parametrize("mode", [AUTO, EXACT])
+def test_sparse_real_descriptors(mode):
+    """Descriptors as the extractor makes them (coarse levels have 1-10 non-zeros, exact duplicates occur)."""
+    O, S = _mods()
+    from sfmfromscratch_b200.synth import second_view, synth_image
+    a = synth_image(480, 640, 0)
+    b = second_view(a, 1)
+    da = S.ScaleRotInvSIFT(a, {}).extract_descriptors()
+    db = S.ScaleRotInvSIFT(b, {}).extract_descriptors()
+    for thr in (0.8, 0.85):
+        m, c = S.NNRatioFeatureMatcher(thr, mode=mode).match_features_ratio_test(da, db)
+        mo, co = O.NNRatioFeatureMatcher(thr).match_features_ratio_test(da, db)
+        assert len(mo) > 100
+        assert_matches_identical(m, c, mo, co)
+
+
+def test_error_behaviour():
+    _, S = _mods()
+    z = np.zeros((4, 128), np.float32)
+    with pytest.raises(IndexError):
+        S.NNRatioFeatureMatcher().match_features_ratio_test(z, z[:1])
+    m, c = S.NNRatioFeatureMatcher().match_features_ratio_test(z, z)     # all distances 0: d1 > 0 fails
+    assert m.shape == (0,) and c.shape == (0,)
+    with pytest.raises(ValueError):
+        S.NNRatioFeatureMatcher().match_features_ratio_test(np.zeros((4, 64), np.float32), np.zeros((4, 64), np.float32))
+
+
+def test_batch_api_equals_single():
+    import torch
+    _, S = _mods()
+    from sfmfromscratch_b200.synth import synth_descriptor_base, synth_descriptors
+    base = synth_descriptor_base(900)
+    sets = [synth_descriptors(n, i, base=base) for i, n in enumerate((900, 640, 777, 2))]
+    nmax = 900
+    desc = torch.zeros((4, nmax, 128), dtype=torch.float32, device='cuda')
+    for i, s in enumerate(sets):
+        desc[i, :len(s)] = torch.from_numpy(s).cuda()
+    counts = torch.tensor([len(s) for s in sets], dtype=torch.int32, device='cuda')
+    pl = [(0, 1), (1, 0), (0, 2), (2, 1), (1, 3), (2, 2)]
+    pairs = torch.tensor(pl, dtype=torch.int32, device='cuda')
+    m, c, cnt, st = S.match_batch_device(desc, counts, pairs, 0.8, want_stats=True)
+    cnt = cnt.cpu().numpy()
+    for k, (i, j) in enumerate(pl):
+        ms, cs = S.NNRatioFeatureMatcher(0.8).match_features_ratio_test(sets[i], sets[j])
+        assert cnt[k] == len(ms)
+        if len(ms):
+            assert np.array_equal(m[k, :cnt[k]].cpu().numpy().astype(np.int64), ms)
+            assert np.array_equal(c[k, :cnt[k]].cpu().numpy(), cs)
+    # a set matched with itself: every row's nearest neighbour is itself at distance 0
+    k = pl.index((2, 2))
+    mm = m[k, :cnt[k]].cpu().numpy()
+    assert np.array_equal(mm[:, 0], mm[:, 1]) and np.all(c[k, :cnt[k]].cpu().numpy() == 0)
+
+
+def test_full_size_8192_auto_equals_exact_and_oracle_sample():
+    """configs[4] pair shape (8192 x 8192): the tensor-core path equals the exact
+    float32 scan (two independent CUDA paths), and a 256-row sample equals the oracle."""
+    import torch
+    O, S = _mods()
+    from sfmfromscratch_b200.synth import synth_descriptor_base, synth_descriptors
+    base = synth_descriptor_base(8192)
+    f1 = synth_descriptors(8192, 0, base=base)
+    f2 = synth_descriptors(8192, 1, base=base)
+    d1, d2 = torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda()
+    out = []
+    for mode in (AUTO, EXACT):
+        m, c, cnt = S.match_device(d1, d2, 0.8, mode)
+        k = int(cnt.cpu()[0])
+        out.append((m[:k].cpu().numpy().astype(np.int64), c[:k].cpu().numpy()))
+    assert len(out[0][0]) > 1000
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    rows = np.arange(0, 8192, 32)
+    mo, co = O.NNRatioFeatureMatcher(0.8).match_features_ratio_test(f1[rows], f2)
+    sel = np.isin(out[0][0][:, 0], rows)
+    mg = out[0][0][sel].copy()
+    mg[:, 0] = np.searchsorted(rows, mg[:, 0])
+    assert_matches_identical(mg, out[0][1][sel], mo, co)
