@@ -2,18 +2,18 @@
 #pragma once
 #include "common.cuh"
 
-#define SFM_HIST1_BINS 4096      // pass 1: key >> 20
-#define SFM_HIST2_BINS 4096      // pass 2: (key >> 8) & 0xfff
-#define SFM_HIST3_BINS 256       // pass 3: key & 0xff
+#define SFM_HIST1_BINS 4096      // radix-select pass 1 (fused into k_harris): key >> 20
 #define SFM_MAX_FW 32            // feature_width / window side upper bound
 
 struct SegState {                // one per (image, level)
-    uint32_t prefix[2];          // radix-select prefix for the two median ranks
-    uint32_t rank[2];            // remaining rank inside the prefix bucket
+    uint32_t prefix[2];          // 12-bit bucket (key >> 20) holding each of the two median ranks
+    uint32_t rank[2];            // remaining rank inside that bucket
     float    median;
     uint32_t n_cand;             // candidates appended by NMS (may exceed cap)
     uint32_t n_sel;              // selected, border-valid keypoints
-    uint32_t pad;
+    uint32_t med_cnt;            // keys of bucket prefix[0] compacted by k_median_compact (may exceed cap)
+    uint32_t min1;               // smallest key of bucket prefix[1] when it differs from prefix[0]
+    uint32_t pad[7];
 };
 
 struct LevelInfo {
@@ -23,6 +23,9 @@ struct LevelInfo {
     int cand_cap;                // candidate slots
     int resize_mode;             // 0: level 0, 1: exact 2x2 mean, 2: bilinear
     int sel_off;                 // offset of this level inside the per-image sel block
+    int med_cap;                 // slots of the median bucket list
+    int pad1;
+    long long med_off;           // u32 offset inside the per-image median-list block
     long long img_off;           // float offset inside the per-image pyramid block (level >= 1)
     long long r_off;             // float offset inside the per-image R block
     long long cand_off;          // u64 offset inside the per-image candidate block
@@ -35,15 +38,14 @@ struct ExtractPlan {
     int nms_half, G, rot, pad0;
     float alpha;
     int sel_stride;              // sum of per-level k
-    long long pyr_stride, r_stride, cand_stride;
+    long long pyr_stride, r_stride, cand_stride, med_stride;
     LevelInfo lv[SFM_MAX_LEVELS];
     // workspace
     const float* images;
     float* pyr;
     float* R;
     uint32_t* hist1;             // [S][4096]
-    uint32_t* hist2;             // [S][2][4096]
-    uint32_t* hist3;             // [S][2][256]
+    uint32_t* med;               // [B][med_stride] keys of the median bucket
     SegState* seg;               // [S]
     unsigned long long* cand;    // [B][cand_stride]
     unsigned long long* sel;     // [B][sel_stride]
@@ -53,6 +55,9 @@ struct ExtractPlan {
 };
 
 struct GaussWeights { float w[SFM_MAX_GAUSS * SFM_MAX_GAUSS]; };
+// Window weights paired for the two output rows a thread owns: entry [jj][dx] =
+// (w[jj][dx] or 0 when jj == G,  w[jj-1][dx] or 0 when jj == 0), jj = 0..G.
+struct GaussPairs { float2 w[(SFM_MAX_GAUSS + 1) * SFM_MAX_GAUSS]; };
 
 struct ExtractOut {
     int32_t *x, *y, *lx, *ly, *level;
