@@ -49,39 +49,45 @@ __global__ void k_match_setup(const __grid_constant__ MatchPlan P) {
 // Warp per row: fp16 copy for the tensor-core pass, |b|^2 and the norms the
 // re-check's error bound needs.
 __global__ void __launch_bounds__(256) k_match_prep(const __grid_constant__ MatchPlan P) {
+    __shared__ float s_max[3][8];
     const int s = blockIdx.y;
-    const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (r >= P.nmax_pad) return;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = blockIdx.x * 8 + warp;
     const int cnt = P.set_cnt[s];
-    const size_t orow = (size_t)s * P.nmax_pad + r;
-    __half2* out = reinterpret_cast<__half2*>(P.h16 + orow * SFM_DESC_DIM + lane * 4);
-    if (r >= cnt) {
-        out[0] = __floats2half2_rn(0.f, 0.f);
-        out[1] = __floats2half2_rn(0.f, 0.f);
-        if (lane == 0) { P.nb[orow] = MT_SENTINEL; P.hatn[orow] = 0.f; P.resn[orow] = 0.f; }
-        return;
+    float hs = 0.f, rs = 0.f, nbv = 0.f;
+    if (r < P.nmax_pad) {
+        const size_t orow = (size_t)s * P.nmax_pad + r;
+        __half2* out = reinterpret_cast<__half2*>(P.h16 + orow * SFM_DESC_DIM + lane * 4);
+        if (r >= cnt) {
+            out[0] = __floats2half2_rn(0.f, 0.f);
+            out[1] = __floats2half2_rn(0.f, 0.f);
+            if (lane == 0) { P.nb[orow] = MT_SENTINEL; P.hatn[orow] = 0.f; P.resn[orow] = 0.f; }
+        } else {
+            const float4 v = *reinterpret_cast<const float4*>(P.set_ptr[s] + (size_t)r * SFM_DESC_DIM + lane * 4);
+            const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+            out[0] = h01; out[1] = h23;
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            float nb = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+            float hn = f01.x * f01.x + f01.y * f01.y + f23.x * f23.x + f23.y * f23.y;
+            float e0 = v.x - f01.x, e1 = v.y - f01.y, e2 = v.z - f23.x, e3 = v.w - f23.y;
+            float rn = e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
+            for (int o = 16; o > 0; o >>= 1) {
+                nb += __shfl_xor_sync(0xffffffffu, nb, o);
+                hn += __shfl_xor_sync(0xffffffffu, hn, o);
+                rn += __shfl_xor_sync(0xffffffffu, rn, o);
+            }
+            hs = sqrtf(hn); rs = sqrtf(rn); nbv = nb;
+            if (lane == 0) { P.nb[orow] = nb; P.hatn[orow] = hs; P.resn[orow] = rs; }
+        }
     }
-    const float4 v = *reinterpret_cast<const float4*>(P.set_ptr[s] + (size_t)r * SFM_DESC_DIM + lane * 4);
-    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
-    out[0] = h01; out[1] = h23;
-    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-    float nb = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-    float hn = f01.x * f01.x + f01.y * f01.y + f23.x * f23.x + f23.y * f23.y;
-    float e0 = v.x - f01.x, e1 = v.y - f01.y, e2 = v.z - f23.x, e3 = v.w - f23.y;
-    float rn = e0 * e0 + e1 * e1 + e2 * e2 + e3 * e3;
-    for (int o = 16; o > 0; o >>= 1) {
-        nb += __shfl_xor_sync(0xffffffffu, nb, o);
-        hn += __shfl_xor_sync(0xffffffffu, hn, o);
-        rn += __shfl_xor_sync(0xffffffffu, rn, o);
-    }
-    if (lane == 0) {
-        const float hs = sqrtf(hn), rs = sqrtf(rn);
-        P.nb[orow] = nb; P.hatn[orow] = hs; P.resn[orow] = rs;
+    // one atomic per CTA and statistic (per-row atomics on three addresses serialise in L2)
+    if (lane == 0) { s_max[0][warp] = hs; s_max[1][warp] = rs; s_max[2][warp] = nbv; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float m = 0.f;
+        for (int w = 0; w < 8; ++w) m = fmaxf(m, s_max[threadIdx.x][w]);
         // non-negative floats order like their bit patterns
-        atomicMax(reinterpret_cast<int*>(P.setmax + 4 * s + 0), __float_as_int(hs));
-        atomicMax(reinterpret_cast<int*>(P.setmax + 4 * s + 1), __float_as_int(rs));
-        atomicMax(reinterpret_cast<int*>(P.setmax + 4 * s + 2), __float_as_int(nb));
+        if (m > 0.f) atomicMax(reinterpret_cast<int*>(P.setmax + 4 * s + threadIdx.x), __float_as_int(m));
     }
 }
 
@@ -160,45 +166,52 @@ __global__ void __launch_bounds__(256) k_match_recheck(const __grid_constant__ M
 
     Top2 best = {INFINITY, -1, INFINITY};
     int visited = 0;
-    for (;;) {
-        // smallest unvisited entry across the warp
+
+    // smallest unvisited entry across the warp (marks it visited); false when none is left
+    auto pop_min = [&](float& wv, uint32_t& wc) -> bool {
         float bv = INFINITY; uint32_t bc = 0; int bi = -1;
 #pragma unroll
         for (int i = 0; i < 4; ++i) if (val[i] < bv) { bv = val[i]; bc = code[i]; bi = i; }
-        float wv = bv; int wl = (bi >= 0) ? lane : 64;
+        wv = bv;
+        int wl = (bi >= 0) ? lane : 64;
         for (int o = 16; o > 0; o >>= 1) {
-            float ov = __shfl_xor_sync(0xffffffffu, wv, o);
-            int ol = __shfl_xor_sync(0xffffffffu, wl, o);
+            const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+            const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
             if (ov < wv || (ov == wv && ol < wl)) { wv = ov; wl = ol; }
         }
-        if (wl >= 32) break;                                 // nothing left
-        const double bound = (double)wv + na - (e_base + q_rel * fabs((double)wv));
-        if (bound > (double)best.d1) break;                  // the rest cannot matter
-        const uint32_t wc = __shfl_sync(0xffffffffu, bc, wl);
-        if (lane == wl) {                                    // mark visited (static indexing)
+        if (wl >= 32) return false;
+        wc = __shfl_sync(0xffffffffu, bc, wl);
+        if (lane == wl) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) if (i == bi) val[i] = INFINITY;
         }
+        return true;
+    };
+    auto group_col = [&](uint32_t wc) -> int {
         const int list = (int)(wc >> MT_IDX_BITS);
         const int split = list >> 1, half = list & 1;
         const int tile = split * P.tiles_per_split + (int)((wc & MT_IDX_MASK) >> 4);
-        const int col = tile * MT_COLS + half * 64 + (int)(wc & 15u) * MT_GROUP + team;
-        const int colc = col < n2 ? col : n2 - 1;            // clamp: every lane runs the same shuffles
-        float d2;
-        {
-            const float* b = B + (size_t)colc * SFM_DESC_DIM + j;
-            float t0 = __fsub_rn(a[0], b[0]);
-            float r = __fmul_rn(t0, t0);
+        return tile * MT_COLS + half * 64 + (int)(wc & 15u) * MT_GROUP + team;
+    };
+    // numpy-order partial sum of this lane's accumulator r[j] against column `colc`
+    auto lane_acc = [&](int colc) -> float {
+        const float* bq = B + (size_t)colc * SFM_DESC_DIM + j;
+        const float t0 = __fsub_rn(a[0], bq[0]);
+        float r = __fmul_rn(t0, t0);
 #pragma unroll
-            for (int m = 1; m < 16; ++m) {
-                float tt = __fsub_rn(a[m], b[8 * m]);
-                r = __fadd_rn(r, __fmul_rn(tt, tt));
-            }
-            r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));   // (r0+r1) ...
-            r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));   // (r0+r1)+(r2+r3)
-            r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));   // full tree
-            d2 = r;
+        for (int m = 1; m < 16; ++m) {
+            const float tt = __fsub_rn(a[m], bq[8 * m]);
+            r = __fadd_rn(r, __fmul_rn(tt, tt));
         }
+        return r;
+    };
+    auto tree = [&](float r) -> float {
+        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));   // (r0+r1) ...
+        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));   // (r0+r1)+(r2+r3)
+        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));   // full tree
+        return r;
+    };
+    auto push_group = [&](float d2, int col) {
 #pragma unroll
         for (int tm = 0; tm < 4; ++tm) {
             const float dd = __shfl_sync(0xffffffffu, d2, tm * 8);
@@ -206,6 +219,36 @@ __global__ void __launch_bounds__(256) k_match_recheck(const __grid_constant__ M
             if (cc < n2) top2_push(best, dd, cc);
         }
         ++visited;
+    };
+
+    // The two best entries are evaluated together (their loads overlap): the second one is needed
+    // in practice anyway, because four columns rarely certify a row.
+    float wv1, wv2; uint32_t wc1 = 0, wc2 = 0;
+    const bool have1 = pop_min(wv1, wc1);
+    const bool have2 = have1 && pop_min(wv2, wc2);
+    if (have2) {
+        const int col1 = group_col(wc1), col2 = group_col(wc2);
+        const float r1 = lane_acc(col1 < n2 ? col1 : n2 - 1);
+        const float r2 = lane_acc(col2 < n2 ? col2 : n2 - 1);
+        push_group(tree(r1), col1);
+        push_group(tree(r2), col2);
+    } else if (have1) {
+        const int col1 = group_col(wc1);
+        push_group(tree(lane_acc(col1 < n2 ? col1 : n2 - 1)), col1);
+    }
+    for (;;) {
+        float wv; uint32_t wc;
+        // peek: the stop test needs the smallest remaining value before it is consumed
+        float pv = INFINITY;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pv = fminf(pv, val[i]);
+        for (int o = 16; o > 0; o >>= 1) pv = fminf(pv, __shfl_xor_sync(0xffffffffu, pv, o));
+        if (pv == INFINITY) break;                            // nothing left
+        const double bound = (double)pv + na - (e_base + q_rel * fabs((double)pv));
+        if (bound > (double)best.d1) break;                   // the rest cannot matter
+        if (!pop_min(wv, wc)) break;
+        const int col = group_col(wc);
+        push_group(tree(lane_acc(col < n2 ? col : n2 - 1)), col);
     }
     const bool certified =
         (Lmin == INFINITY) ||

@@ -60,10 +60,15 @@ def _stream_ptr() -> int:
 
 
 def extract_batch_device(images: torch.Tensor, params: N.SfmExtractParams, *, want_aux: bool = True,
-                         device_index: Optional[int] = None) -> Dict[str, torch.Tensor]:
+                         device_index: Optional[int] = None, out: Optional[Dict[str, torch.Tensor]] = None,
+                         check: bool = True) -> Dict[str, torch.Tensor]:
     """Run sfm_extract_batch on a float32 CUDA tensor [B, H, W].  Returns device
-    tensors: x, y, count, desc (+ lx, ly, level, conf when want_aux).  Asynchronous
-    on the current stream except for the overflow check (one 4-byte read)."""
+    tensors: x, y, count, desc (+ lx, ly, level, conf when want_aux).  `out` may
+    hold preallocated (contiguous) result tensors, e.g. batch slices of larger
+    ones.  Asynchronous on the current stream; with check=True (default) the
+    candidate-overflow flag is read back (a 4-byte copy and a stream sync) and a
+    plateau image is retried with full-size buffers, with check=False the caller
+    does that later through check_extract_status(result)."""
     if not images.is_cuda or images.dtype != torch.float32 or images.dim() != 3:
         raise ValueError("images must be a float32 CUDA tensor of shape [B, H, W]")
     images = images.contiguous()
@@ -75,15 +80,21 @@ def extract_batch_device(images: torch.Tensor, params: N.SfmExtractParams, *, wa
     with torch.cuda.device(dev):
         cap = L.sfm_extract_max_keypoints(C.byref(params))
         i32 = dict(dtype=torch.int32, device=dev)
-        out = {
-            'x': torch.empty((B, cap), **i32), 'y': torch.empty((B, cap), **i32),
-            'count': torch.empty((B,), **i32),
-            'desc': torch.empty((B, cap, N.DESC_DIM), dtype=torch.float32, device=dev),
-        }
-        if want_aux:
-            out.update(lx=torch.empty((B, cap), **i32), ly=torch.empty((B, cap), **i32),
-                       level=torch.empty((B, cap), **i32),
-                       conf=torch.empty((B, cap), dtype=torch.float32, device=dev))
+        if out is None:
+            out = {
+                'x': torch.empty((B, cap), **i32), 'y': torch.empty((B, cap), **i32),
+                'count': torch.empty((B,), **i32),
+                'desc': torch.empty((B, cap, N.DESC_DIM), dtype=torch.float32, device=dev),
+            }
+            if want_aux:
+                out.update(lx=torch.empty((B, cap), **i32), ly=torch.empty((B, cap), **i32),
+                           level=torch.empty((B, cap), **i32),
+                           conf=torch.empty((B, cap), dtype=torch.float32, device=dev))
+        else:
+            for k in ('x', 'y', 'count', 'desc'):
+                if not out[k].is_contiguous() or out[k].shape[0] != B:
+                    raise ValueError(f"out[{k!r}] must be contiguous with leading dimension {B}")
+            cap = out['x'].shape[1]
         ptr = lambda k: out[k].data_ptr() if k in out else None
         for attempt in range(2):
             nbytes = L.sfm_extract_workspace_bytes(B, H, W, C.byref(params))
@@ -97,6 +108,9 @@ def extract_batch_device(images: torch.Tensor, params: N.SfmExtractParams, *, wa
             N.check(L.sfm_extract_batch(ctx, _stream_ptr(), images.data_ptr(), B, H, W, C.byref(params),
                                         ws.data_ptr(), nbytes, ptr('x'), ptr('y'), ptr('lx'), ptr('ly'),
                                         ptr('level'), ptr('conf'), ptr('desc'), ptr('count'), cap), ctx)
+            if not check:
+                out['_flag'] = ws[:4].view(torch.int32).clone()    # overflow flag, read by check_extract_status
+                break
             rc = L.sfm_extract_status(ctx, _stream_ptr(), ws.data_ptr())
             if rc == N.SFM_ERR_CAPACITY and attempt == 0 and not params.cand_full:
                 params.cand_full = 1          # plateau image: one candidate slot per pixel
@@ -104,6 +118,13 @@ def extract_batch_device(images: torch.Tensor, params: N.SfmExtractParams, *, wa
             N.check(rc, ctx)
             break
     return out
+
+
+def check_extract_status(result: Dict[str, torch.Tensor]) -> bool:
+    """For check=False calls: True when no candidate buffer overflowed (the
+    result is valid); False means re-run with params.cand_full = 1."""
+    f = result.get('_flag')
+    return True if f is None else int(f.cpu()[0]) == 0
 
 
 def _to_device(image: np.ndarray) -> torch.Tensor:

@@ -75,6 +75,7 @@ class FeaturePipeline:
         self.params, self._keep = make_params(extractor_params, pyramid=True)
         self.ratio_threshold = ratio_threshold
         self.rank, self.world, self.group = rank, world, group
+        self.pair_block = 64
 
     def extract(self, images: torch.Tensor):
         from .extractor import extract_batch_device
@@ -89,10 +90,70 @@ class FeaturePipeline:
             return None
         return match_batch_device(desc_all, counts_all, pairs, self.ratio_threshold, cap=cap)
 
+    def run_host(self, host_images: torch.Tensor, pairs_global: np.ndarray, host_out: dict, chunk: int = 8):
+        """The hot path end to end from HOST buffers: `host_images` is a pinned
+        float32 [B, H, W] tensor, `host_out` holds pinned result tensors
+        (x, y, desc, count [, matches, conf, mcount]).  The batch is cut into
+        chunks; chunk i+1's host-to-device copy and chunk i-1's device-to-host
+        copy run on their own streams while chunk i is being extracted, so the
+        PCIe transfers overlap the kernels (both DMA directions are independent).
+        Returns after everything has landed in `host_out`."""
+        from .extractor import check_extract_status, extract_batch_device
+        dev = torch.device('cuda', torch.cuda.current_device())
+        main = torch.cuda.current_stream()
+        if not hasattr(self, '_s_in'):
+            self._s_in, self._s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        B, H, W = host_images.shape
+        cap = host_out['x'].shape[1]
+        imgs = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        i32 = dict(dtype=torch.int32, device=dev)
+        full = {'x': torch.empty((B, cap), **i32), 'y': torch.empty((B, cap), **i32),
+                'count': torch.empty((B,), **i32),
+                'desc': torch.empty((B, cap, 128), dtype=torch.float32, device=dev)}
+        self._s_in.wait_stream(main)                 # the allocations above are stream-ordered on `main`
+        self._s_out.wait_stream(main)
+        bounds = [(c0, min(c0 + chunk, B)) for c0 in range(0, B, chunk)]
+        ready = []
+        with torch.cuda.stream(self._s_in):
+            for c0, c1 in bounds:
+                imgs[c0:c1].copy_(host_images[c0:c1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._s_in)
+                ready.append(ev)
+        flags = []
+        for (c0, c1), ev in zip(bounds, ready):
+            main.wait_event(ev)
+            res = extract_batch_device(imgs[c0:c1], self.params, want_aux=False, check=False,
+                                       out={k: v[c0:c1] for k, v in full.items()})
+            flags.append(res)
+            done = torch.cuda.Event()
+            done.record(main)
+            self._s_out.wait_event(done)
+            with torch.cuda.stream(self._s_out):
+                for k in ('x', 'y', 'desc', 'count'):
+                    host_out[k][c0:c1].copy_(full[k][c0:c1], non_blocking=True)
+        desc_all, counts_all = self.exchange(full['desc'], full['count'])
+        mine = deal_pairs(pairs_global, self.rank, self.world, block=self.pair_block)
+        if len(mine):
+            pairs = torch.from_numpy(np.ascontiguousarray(mine)).to(dev, non_blocking=True)
+            m = self.match(desc_all, counts_all, pairs, cap=host_out['matches'].shape[1])
+            host_out['matches'][:len(mine)].copy_(m[0], non_blocking=True)
+            host_out['conf'][:len(mine)].copy_(m[1], non_blocking=True)
+            host_out['mcount'][:len(mine)].copy_(m[2], non_blocking=True)
+        main.wait_stream(self._s_out)
+        for t in (imgs, *full.values()):
+            t.record_stream(self._s_in); t.record_stream(self._s_out)
+        main.synchronize()
+        if not all(check_extract_status(r) for r in flags):
+            # plateau image somewhere in the batch: redo it with full-size candidate buffers
+            self.params.cand_full = 1
+            return self.run_host(host_images, pairs_global, host_out, chunk)
+        return len(mine)
+
     def step(self, images: torch.Tensor, pairs_global: np.ndarray):
         """Extract the local images, all-gather, match this rank's share of `pairs_global`."""
         out = self.extract(images)
         desc_all, counts_all = self.exchange(out['desc'], out['count'])
-        mine = deal_pairs(pairs_global, self.rank, self.world)
+        mine = deal_pairs(pairs_global, self.rank, self.world, block=self.pair_block)
         pairs = torch.from_numpy(np.ascontiguousarray(mine)).to(images.device)
         return out, self.match(desc_all, counts_all, pairs)
