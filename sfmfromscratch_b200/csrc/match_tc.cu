@@ -110,7 +110,7 @@ __device__ __forceinline__ UnitInfo decode_unit(const MatchPlan& P, int unit) {
     u.split = unit % P.n_splits;
     const int q = unit / P.n_splits;
     u.rb = q % rowblocks;
-    u.p = q / rowblocks;
+    u.p = P.p0 + q / rowblocks;
     u.qa = P.pairs[2 * u.p]; u.qb = P.pairs[2 * u.p + 1];
     u.n1 = P.set_cnt[u.qa]; u.n2 = P.set_cnt[u.qb];
     const int ntiles = (u.n2 + MT_COLS - 1) / MT_COLS;
@@ -336,7 +336,7 @@ int launch_match_tc(SfmCtx* ctx, cudaStream_t st, const MatchPlan& P) {
                                                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sfm_set_error(ctx, SFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-    const int n_units = P.n_pairs * (P.nmax_pad / MT_ROWS) * P.n_splits;
+    const int n_units = P.pn * (P.nmax_pad / MT_ROWS) * P.n_splits;
     SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     const int grid = n_units < ctx->sm_count ? n_units : ctx->sm_count;
     SFM_LAUNCH(ctx, st, "k_match_tc", k_match_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(P, tmap, n_units));
