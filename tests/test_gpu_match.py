@@ -136,3 +136,29 @@ def test_full_size_8192_auto_equals_exact_and_oracle_sample():
     mg = out[0][0][sel].copy()
     mg[:, 0] = np.searchsorted(rows, mg[:, 0])
     assert_matches_identical(mg, out[0][1][sel], mo, co)
+
+
+def test_4k_pair_20k_descriptors_auto_equals_exact():
+    """configs[2] matching half: ~20 k x 20 k descriptors (three column splits per row block).
+    Both CUDA paths must agree bit for bit; a 128-row sample is checked against the oracle."""
+    import torch
+    O, S = _mods()
+    from sfmfromscratch_b200.synth import synth_descriptor_base, synth_descriptors
+    n1, n2 = 19531, 20007
+    base = synth_descriptor_base(n2)
+    f1 = synth_descriptors(n1, 7, base=base)
+    f2 = synth_descriptors(n2, 8, base=base)
+    d1, d2 = torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda()
+    res = []
+    for mode in (AUTO, EXACT):
+        m, c, cnt = S.match_device(d1, d2, 0.8, mode)
+        k = int(cnt.cpu()[0])
+        res.append((m[:k].cpu().numpy().astype(np.int64), c[:k].cpu().numpy()))
+    assert len(res[0][0]) > 3000
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    rows = np.arange(0, n1, 153)
+    mo, co = O.NNRatioFeatureMatcher(0.8).match_features_ratio_test(f1[rows], f2)
+    sel = np.isin(res[0][0][:, 0], rows)
+    mg = res[0][0][sel].copy()
+    mg[:, 0] = np.searchsorted(rows, mg[:, 0])
+    assert_matches_identical(mg, res[0][1][sel], mo, co)
