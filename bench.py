@@ -212,10 +212,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    pipe = PL.FeaturePipeline({}, RATIO, rank=rank, world=world)
+    pipe.pair_block = 4
+
     def step(imgs):
-        out = extract_batch_device(imgs, params, want_aux=False)
-        d_all, c_all = PL.gather_descriptors(out['desc'], out['count'])
-        m = match_batch_device(d_all, c_all, my_pairs, RATIO, cap=2500) if n_my_pairs else None
+        out = pipe.extract(imgs)
+        d_all, c_all = pipe.exchange(out['desc'], out['count'])
+        m = pipe.match(d_all, c_all, my_pairs, cap=2500, pairs_host=my_pairs_np) if n_my_pairs else None
         return out, m
 
     def timed(fn, steps, warmup):
@@ -283,8 +286,6 @@ def run_ours(args):
     h_mc = torch.empty((max(n_my_pairs, 1), cap), dtype=torch.float32).pin_memory()
     h_mn = torch.empty((max(n_my_pairs, 1),), dtype=torch.int32).pin_memory()
 
-    pipe = PL.FeaturePipeline({}, RATIO, rank=rank, world=world)
-    pipe.pair_block = 4
     host_out = {'x': h_x, 'y': h_y, 'desc': h_d, 'count': h_c, 'matches': h_m, 'conf': h_mc, 'mcount': h_mn}
 
     def e2e_step():
@@ -335,6 +336,33 @@ def run_ours(args):
                           "peak_source": pk["src"] + ", sustained bf16 (fp16 runs at the same rate)",
                           "flops": "256 per descriptor pair (algorithmic == executed: single fp16 pass)"}}
 
+    # ---- configs[1] literally: ONE 1080p image (latency-bound: 47 MB of traffic, ~25 launches)
+    single = None
+    if rank == 0:
+        from sfmfromscratch_b200 import ScaleRotInvSIFT
+        one = images[:1]
+        for _ in range(3):
+            extract_batch_device(one, params, want_aux=False)
+        torch.cuda.synchronize()
+        a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a1.record()
+        for _ in range(20):
+            extract_batch_device(one, params, want_aux=False)
+        b1.record()
+        torch.cuda.synchronize()
+        lat = a1.elapsed_time(b1) / 20
+        img_np = base_imgs[0]
+        ScaleRotInvSIFT(img_np, {})
+        t0 = time.time()
+        for _ in range(5):
+            e = ScaleRotInvSIFT(img_np, {})
+        host_ms = (time.time() - t0) / 5 * 1e3
+        single = {"workload": "one 1920x1080 image, ScaleRotInvSIFT defaults (configs[1])",
+                  "resident_ms": lat, "resident_mpixel_per_s": IMG_H * IMG_W / (lat * 1e-3) / 1e6,
+                  "class_call_ms": host_ms, "class_call_mpixel_per_s": IMG_H * IMG_W / (host_ms * 1e-3) / 1e6,
+                  "keypoints": int(len(e.detect_keypoints()[0])),
+                  "note": "class_call = ScaleRotInvSIFT(numpy image, {}) -> numpy keypoints/descriptors, pageable host memory"}
+
     # ---- CPU baseline on a bounded sample (rank 0, N == 1 only)
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:
@@ -354,7 +382,8 @@ def run_ours(args):
                            "l2": "inputs larger than L2 (265 MB of images, 352 MB of R planes per step)",
                            "parallelism": f"image shards x{world}, descriptor all-gather (NCCL), pair shards"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-                "clocks": sampler.summary(), "ms_per_step_unprofiled": plain_ms, "kernels": kernels, "match": match}
+                "clocks": sampler.summary(), "ms_per_step_unprofiled": plain_ms, "kernels": kernels, "match": match,
+                "single_image": single}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

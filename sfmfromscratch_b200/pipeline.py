@@ -84,10 +84,21 @@ class FeaturePipeline:
     def exchange(self, desc: torch.Tensor, counts: torch.Tensor):
         return gather_descriptors(desc, counts, self.group)
 
-    def match(self, desc_all: torch.Tensor, counts_all: torch.Tensor, pairs: torch.Tensor, cap: Optional[int] = None):
+    def match(self, desc_all: torch.Tensor, counts_all: torch.Tensor, pairs: torch.Tensor, cap: Optional[int] = None,
+              pairs_host: Optional[np.ndarray] = None):
+        """Match `pairs` (ids into desc_all).  When this rank's pairs touch only a fraction of the
+        gathered sets (pair sharding), the referenced blocks are compacted first so the matcher's
+        per-set preparation does not run over every rank's descriptors."""
         from .matcher import match_batch_device
         if pairs.shape[0] == 0:
             return None
+        if pairs_host is not None and desc_all.shape[0] > 1:
+            ids, inv = np.unique(pairs_host.reshape(-1), return_inverse=True)
+            if len(ids) <= 0.6 * desc_all.shape[0]:
+                idx = torch.from_numpy(ids.astype(np.int64)).to(desc_all.device, non_blocking=True)
+                desc_all = desc_all.index_select(0, idx)
+                counts_all = counts_all.index_select(0, idx)
+                pairs = torch.from_numpy(inv.reshape(-1, 2).astype(np.int32)).to(desc_all.device, non_blocking=True)
         return match_batch_device(desc_all, counts_all, pairs, self.ratio_threshold, cap=cap)
 
     def run_host(self, host_images: torch.Tensor, pairs_global: np.ndarray, host_out: dict, chunk: int = 8):
@@ -136,7 +147,7 @@ class FeaturePipeline:
         mine = deal_pairs(pairs_global, self.rank, self.world, block=self.pair_block)
         if len(mine):
             pairs = torch.from_numpy(np.ascontiguousarray(mine)).to(dev, non_blocking=True)
-            m = self.match(desc_all, counts_all, pairs, cap=host_out['matches'].shape[1])
+            m = self.match(desc_all, counts_all, pairs, cap=host_out['matches'].shape[1], pairs_host=mine)
             host_out['matches'][:len(mine)].copy_(m[0], non_blocking=True)
             host_out['conf'][:len(mine)].copy_(m[1], non_blocking=True)
             host_out['mcount'][:len(mine)].copy_(m[2], non_blocking=True)
@@ -156,4 +167,4 @@ class FeaturePipeline:
         desc_all, counts_all = self.exchange(out['desc'], out['count'])
         mine = deal_pairs(pairs_global, self.rank, self.world, block=self.pair_block)
         pairs = torch.from_numpy(np.ascontiguousarray(mine)).to(images.device)
-        return out, self.match(desc_all, counts_all, pairs)
+        return out, self.match(desc_all, counts_all, pairs, pairs_host=mine)
