@@ -54,7 +54,10 @@ struct ExtractPlan {
     double e37[37];              // np.linspace(-pi, pi, 37)
 };
 
-struct GaussWeights { float w[SFM_MAX_GAUSS * SFM_MAX_GAUSS]; };
+// Window weights, one row of the G x G kernel per 16 floats (64-byte aligned rows: the rolled
+// tap-row loop of k_harris fetches a row with vector constant loads).
+#define SFM_GW_PITCH 16
+struct __align__(16) GaussWeights { float w[SFM_MAX_GAUSS * SFM_GW_PITCH]; };
 // Window weights paired for the two output rows a thread owns: entry [jj][dx] =
 // (w[jj][dx] or 0 when jj == G,  w[jj-1][dx] or 0 when jj == 0), jj = 0..G.
 struct GaussPairs { float2 w[(SFM_MAX_GAUSS + 1) * SFM_MAX_GAUSS]; };
