@@ -65,6 +65,32 @@ def gather_descriptors(desc: torch.Tensor, counts: torch.Tensor, group=None):
     return out_d, out_c
 
 
+class GraphedExtractor:
+    """sfm_extract_batch for a fixed batch shape captured once into a CUDA graph: the ~25 kernel
+    launches of an extraction replay as one submission (what matters for a single image, where
+    launch latency, not bandwidth, sets the time).  `sample` is a representative float32 CUDA
+    batch [B, H, W]; run(images) copies into the static input and replays; results are the
+    static output tensors (valid until the next run)."""
+
+    def __init__(self, sample: torch.Tensor, extractor_params: Optional[dict] = None, pyramid: bool = True):
+        from .extractor import check_extract_status, extract_batch_device, make_params
+        self.params, self._keep = make_params(extractor_params, pyramid=pyramid)
+        self.static_in = sample.clone()
+        extract_batch_device(self.static_in, self.params, want_aux=False)          # warm-up; sizes candidate buffers
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = extract_batch_device(self.static_in, self.params, want_aux=False, check=False)
+        self._check = check_extract_status
+
+    def run(self, images: torch.Tensor, check: bool = False):
+        self.static_in.copy_(images, non_blocking=True)
+        self.graph.replay()
+        if check and not self._check(self.out):
+            raise RuntimeError("candidate buffer overflow in a graphed extraction: rebuild with cand_full")
+        return self.out
+
+
 class FeaturePipeline:
     """Extraction of this rank's image shard, descriptor exchange, matching of
     this rank's pair share.  All tensors stay on the device."""
