@@ -134,7 +134,10 @@ class FeaturePipeline:
         chunks; chunk i+1's host-to-device copy and chunk i-1's device-to-host
         copy run on their own streams while chunk i is being extracted, so the
         PCIe transfers overlap the kernels (both DMA directions are independent).
-        Returns after everything has landed in `host_out`."""
+        (Measured and dropped: tapering the chunk sizes and matching pairs incrementally as their
+        images finish -- with ~25 launches per chunk the host enqueue rate, not the tail, becomes the
+        limit: 6.2-6.6 ms against 5.9 ms.)  Returns this rank's pair list, in the order of the rows of
+        host_out['matches'], after everything has landed in `host_out`."""
         from .extractor import check_extract_status, extract_batch_device
         dev = torch.device('cuda', torch.cuda.current_device())
         main = torch.cuda.current_stream()
@@ -172,7 +175,7 @@ class FeaturePipeline:
         desc_all, counts_all = self.exchange(full['desc'], full['count'])
         mine = deal_pairs(pairs_global, self.rank, self.world, block=self.pair_block)
         if len(mine):
-            pairs = torch.from_numpy(np.ascontiguousarray(mine)).to(dev, non_blocking=True)
+            pairs = torch.from_numpy(np.ascontiguousarray(mine)).pin_memory().to(dev, non_blocking=True)
             m = self.match(desc_all, counts_all, pairs, cap=host_out['matches'].shape[1], pairs_host=mine)
             host_out['matches'][:len(mine)].copy_(m[0], non_blocking=True)
             host_out['conf'][:len(mine)].copy_(m[1], non_blocking=True)
@@ -185,7 +188,7 @@ class FeaturePipeline:
             # plateau image somewhere in the batch: redo it with full-size candidate buffers
             self.params.cand_full = 1
             return self.run_host(host_images, pairs_global, host_out, chunk)
-        return len(mine)
+        return mine
 
     def step(self, images: torch.Tensor, pairs_global: np.ndarray):
         """Extract the local images, all-gather, match this rank's share of `pairs_global`."""

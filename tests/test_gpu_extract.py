@@ -206,3 +206,37 @@ def test_4k_many_keypoints_vs_oracle():
         assert np.all(g.levels[off:off + n] == l)
         off += n
     assert off == len(X)
+
+
+def test_run_host_pipeline_equals_plain_calls():
+    """FeaturePipeline.run_host (chunked, 3 streams, incremental matching) returns exactly what the
+    plain batch calls return."""
+    import torch
+    _, S, _ = _mods()
+    from sfmfromscratch_b200 import pipeline as PL
+    from sfmfromscratch_b200.synth import synth_image
+    B, H, W, cap = 11, 120, 160, 2500
+    imgs = np.stack([synth_image(H, W, 40 + s) for s in range(B)])
+    host = torch.from_numpy(imgs).pin_memory()
+    pairs = PL.consecutive_pairs(B)
+    out = {'x': torch.zeros((B, cap), dtype=torch.int32).pin_memory(), 'y': torch.zeros((B, cap), dtype=torch.int32).pin_memory(),
+           'desc': torch.zeros((B, cap, 128), dtype=torch.float32).pin_memory(), 'count': torch.zeros((B,), dtype=torch.int32).pin_memory(),
+           'matches': torch.zeros((len(pairs), cap, 2), dtype=torch.int32).pin_memory(),
+           'conf': torch.zeros((len(pairs), cap), dtype=torch.float32).pin_memory(),
+           'mcount': torch.zeros((len(pairs),), dtype=torch.int32).pin_memory()}
+    pipe = PL.FeaturePipeline({}, 0.8)
+    order = pipe.run_host(host, pairs, out, chunk=4)
+    ref = S.extract_batch(imgs, {})
+    for b in range(B):
+        n = int(out['count'][b])
+        assert n == len(ref[b][0])
+        assert np.array_equal(out['x'][b, :n].numpy(), ref[b][0]) and np.array_equal(out['y'][b, :n].numpy(), ref[b][1])
+        assert np.array_equal(out['desc'][b, :n].numpy(), ref[b][2])
+    assert sorted(map(tuple, order.tolist())) == sorted(map(tuple, pairs.tolist()))
+    for k, (i, j) in enumerate(order.tolist()):
+        m, c = S.NNRatioFeatureMatcher(0.8).match_features_ratio_test(ref[i][2], ref[j][2])
+        n = int(out['mcount'][k])
+        assert n == len(m)
+        if n:
+            assert np.array_equal(out['matches'][k, :n].numpy().astype(np.int64), m)
+            assert np.array_equal(out['conf'][k, :n].numpy(), c)
