@@ -258,11 +258,12 @@ def run_ours(args):
     kstat = N.profile_collect(local)
     N.profile_enable(False, local)
 
-    # ---- roofline of the dominant kernel (k_harris): 4 B read + 4 B written per pyramid pixel
+    # ---- roofline of the dominant kernel (k_harris)
     lp = level_pixels(IMG_H, IMG_W)
     kh = kstat.get("k_harris", (0, 0.0))
     kh_ms_step = kh[1] / args.steps if kh[1] else float("nan")
-    harris_bytes = 8.0 * lp * BATCH
+    # 4 B read + 4 B written per pyramid pixel, + 4 B per pixel of the next (exactly halved) level it emits
+    harris_bytes = (8.0 * lp + 4.0 * (lp - IMG_H * IMG_W)) * BATCH
     achieved = harris_bytes / (kh_ms_step * 1e-3) / 1e9 if kh[1] else None
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
