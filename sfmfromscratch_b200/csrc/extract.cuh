@@ -57,7 +57,12 @@ struct ExtractPlan {
 // Window weights, one row of the G x G kernel per 16 floats (64-byte aligned rows: the rolled
 // tap-row loop of k_harris fetches a row with vector constant loads).
 #define SFM_GW_PITCH 16
-struct __align__(16) GaussWeights { float w[SFM_MAX_GAUSS * SFM_GW_PITCH]; };
+struct __align__(16) GaussWeights {
+    float w[SFM_MAX_GAUSS * SFM_GW_PITCH];
+    // wp[jj][dx] = (w[jj][dx], w[jj-1][dx]) for jj = 1..G-1: the packed (upper row, lower row) weight
+    // pair of product row jj, consumed as one 64-bit uniform operand by the FFMA2 variant
+    float2 wp[SFM_MAX_GAUSS * SFM_GW_PITCH];
+};
 // Window weights paired for the two output rows a thread owns: entry [jj][dx] =
 // (w[jj][dx] or 0 when jj == G,  w[jj-1][dx] or 0 when jj == 0), jj = 0..G.
 struct GaussPairs { float2 w[(SFM_MAX_GAUSS + 1) * SFM_MAX_GAUSS]; };
