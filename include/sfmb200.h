@@ -14,6 +14,8 @@
  *                            extract_descriptors)
  *   sfm_harris_response      FeatureExtractor/SIFT/NaiveSIFT.py:60-74 (R map only;
  *                            exposed for parity tests)
+ *   sfm_ingest_rgb8          Runner.py:33-46 with :467-493,:551-563 (_load_image ->
+ *                            _PIL_resize -> _rgb2gray), from the decoded 8-bit image
  *   sfm_match_ratio          FeatureMatcher/NNRatioFeatureMatcher.py:8-60
  *                            (match_features_ratio_test)
  *   sfm_match_ratio_batch    the same method over a list of image pairs (the
@@ -156,6 +158,20 @@ SFM_EXPORT int sfm_extract_status(SfmCtx* ctx, void* stream, const void* workspa
 /* Harris response map of one H x W image (NaiveSIFT.py:60-74): r_out [H][W]. */
 SFM_EXPORT int sfm_harris_response(SfmCtx* ctx, void* stream, const float* image_dev, int H, int W,
                         const SfmExtractParams* p, float* r_out);
+
+/* ---- ingest -------------------------------- */
+
+/*
+ * Runner.py:33-46: _load_image (:551-563) -> _PIL_resize (:481-493, PIL's default BICUBIC on
+ * RGB) -> _rgb2gray (:467-478), starting from the decoded 8-bit image.
+ * rgb_dev [B][H][W][3] uint8 (dev) -> gray_out [B][out_h][out_w] float32 (dev), bit-identical
+ * to the array the reference hands to its extractor.  (out_w, out_h) is the reference's
+ * (int(W * scale_factor), int(H * scale_factor)).
+ */
+SFM_EXPORT size_t sfm_ingest_workspace_bytes(int B, int H, int W, int out_h, int out_w);
+SFM_EXPORT int sfm_ingest_rgb8(SfmCtx* ctx, void* stream, const uint8_t* rgb_dev, int B, int H, int W,
+                               int out_h, int out_w, void* workspace_dev, size_t workspace_bytes,
+                               float* gray_out);
 
 /* ---- matching ---------------------------------------------------------- */
 

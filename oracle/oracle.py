@@ -361,3 +361,87 @@ def dist_matrix(features1: np.ndarray, features2: np.ndarray) -> np.ndarray:
     out = np.empty((f1.shape[0], f2.shape[0]), np.float32)
     lib().orc_dist_matrix(_p(f1), f1.shape[0], _p(f2), f2.shape[0], f1.shape[1], _p(out))
     return out
+
+
+# --------------------------------------------------------------------------
+# image ingest
+# --------------------------------------------------------------------------
+
+def ingest_gray(img_u8: np.ndarray, scale_factor: float = 0.5) -> np.ndarray:
+    """Runner.py:33-46 from the decoded image: _load_image (:551-563: float32 / 255), _PIL_resize
+    (:481-493: in-place * 255, np.uint8, PIL's default BICUBIC, float32 / 255), _rgb2gray (:467-478).
+    Pillow is the reference's own dependency for this step, so it is called as the reference calls
+    it; pil_bicubic_resize below restates its algorithm and the tests hold the two together."""
+    import PIL.Image
+    img = np.asarray(img_u8, dtype=float).astype(np.float32) / 255          # _load_image + _im2single
+    size = (int(img.shape[1] * scale_factor), int(img.shape[0] * scale_factor))
+    img *= 255                                                              # _numpy_arr_to_PIL_image
+    pil = PIL.Image.fromarray(np.uint8(img)).resize(size)
+    img = np.asarray(pil).astype(np.float32)
+    img /= 255                                                              # _PIL_image_to_numpy_arr
+    c = [0.299, 0.587, 0.114]
+    return img[:, :, 0] * c[0] + img[:, :, 1] * c[1] + img[:, :, 2] * c[2]   # _rgb2gray
+
+
+def _pil_coeffs(in_size: int, out_size: int):
+    """Pillow libImaging/Resample.c precompute_coeffs + normalize_coeffs_8bpc (BICUBIC, full box)."""
+    import math
+    PB = 32 - 8 - 2
+
+    def bicubic(x):
+        a = -0.5
+        if x < 0.0:
+            x = -x
+        if x < 1.0:
+            return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+        if x < 2.0:
+            return (((x - 5) * x + 8) * x - 4) * a
+        return 0.0
+
+    scale = filterscale = in_size / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds, kk = [], np.zeros((out_size, ksize), np.int64)
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        ss = 1.0 / filterscale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        k = [bicubic((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for w in k:
+            ww += w
+        for x, w in enumerate(k):
+            if ww != 0.0:
+                w = w / ww
+            kk[xx, x] = int(w * (1 << PB) - 0.5) if w < 0 else int(w * (1 << PB) + 0.5)
+        bounds.append((xmin, xmax))
+    return bounds, kk
+
+
+def pil_bicubic_resize(img_u8: np.ndarray, size) -> np.ndarray:
+    """Restatement of PIL.Image.resize(size) for 8-bit RGB: two passes (horizontal, then vertical),
+    22-bit fixed-point coefficients, each pass rounded and clipped to uint8."""
+    PB = 32 - 8 - 2
+    ow, oh = size
+    H, W, C = img_u8.shape
+    bx, kx = _pil_coeffs(W, ow)
+    by, ky = _pil_coeffs(H, oh)
+    a = img_u8.astype(np.int64)
+    tmp = np.zeros((H, ow, C), np.int64)
+    for xx in range(ow):
+        xmin, n = bx[xx]
+        acc = np.full((H, C), 1 << (PB - 1), np.int64)
+        for x in range(n):
+            acc += a[:, xmin + x, :] * kx[xx, x]
+        tmp[:, xx, :] = np.clip(acc >> PB, 0, 255)
+    out = np.zeros((oh, ow, C), np.uint8)
+    for yy in range(oh):
+        ymin, n = by[yy]
+        acc = np.full((ow, C), 1 << (PB - 1), np.int64)
+        for y in range(n):
+            acc += tmp[ymin + y, :, :] * ky[yy, y]
+        out[yy] = np.clip(acc >> PB, 0, 255)
+    return out

@@ -28,6 +28,7 @@ EXPORTS = [
     "sfm_ctx_launch_count", "sfm_profile_enable", "sfm_profile_collect",
     "sfm_extract_default_params", "sfm_extract_max_keypoints", "sfm_extract_workspace_bytes",
     "sfm_extract_batch", "sfm_extract_status", "sfm_harris_response",
+    "sfm_ingest_workspace_bytes", "sfm_ingest_rgb8",
     "sfm_match_workspace_bytes", "sfm_match_ratio", "sfm_match_ratio_batch",
 ]
 
@@ -91,6 +92,9 @@ def load_library() -> C.CDLL:
                                         i32p, i32p, i32p, i32p, i32p, fp, fp, i32p, C.c_int]
         L.sfm_extract_status.argtypes = [vp, vp, vp]
         L.sfm_harris_response.argtypes = [vp, vp, fp, C.c_int, C.c_int, PP, fp]
+        L.sfm_ingest_workspace_bytes.argtypes = [C.c_int] * 5
+        L.sfm_ingest_workspace_bytes.restype = C.c_size_t
+        L.sfm_ingest_rgb8.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, fp]
         L.sfm_match_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
         L.sfm_match_workspace_bytes.restype = C.c_size_t
         L.sfm_match_ratio.argtypes = [vp, vp, fp, C.c_int, fp, C.c_int, C.c_int, C.c_float, C.c_int, vp,

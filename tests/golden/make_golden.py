@@ -100,6 +100,36 @@ def main():
     np.savez_compressed(os.path.join(HERE, "matcher_220x260.npz"), f1=f1, f2=f2, matches=m, conf=c,
                         matches95=m2, conf95=c2)
     out['matcher_220x260'] = dict(matches=int(len(m)), matches95=int(len(m2)))
+    # 6. image ingest: Runner.py's own helpers on an 8-bit RGB image
+    import importlib.util, tempfile, types
+    from PIL import Image
+
+    class _Stub(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return type(name, (), {"__init__": lambda self, *a, **k: None, "__call__": lambda self, *a, **k: None})
+
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.widgets", "matplotlib.cm", "matplotlib.colors",
+                 "mpl_toolkits", "mpl_toolkits.mplot3d"):          # Runner.py imports the (absent) GUI stack
+        if name not in sys.modules:
+            m = _Stub(name); m.__path__ = []; sys.modules[name] = m
+    spec = importlib.util.spec_from_file_location("Runner", os.path.join(REF, "Runner.py"))
+    R = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(R)
+    rng = np.random.default_rng(42)
+    base = rng.integers(0, 256, (40, 52, 3))
+    rgb = np.clip(np.kron(base, np.ones((4, 4, 1)))[:151, :203] + rng.integers(-25, 26, (151, 203, 3)), 0, 255).astype(np.uint8)
+    grays = {}
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "a.png")
+        Image.fromarray(rgb).save(path)
+        for sf in (0.5, 0.3):
+            a = R._load_image(path)                                                    # Runner.py:33
+            a = R._PIL_resize(a, (int(a.shape[1] * sf), int(a.shape[0] * sf)))        # :37-39
+            grays[sf] = R._rgb2gray(a)                                                 # :45
+    np.savez_compressed(os.path.join(HERE, "ingest_151x203.npz"), rgb=rgb, gray05=grays[0.5], gray03=grays[0.3])
+    out['ingest_151x203'] = dict(shape05=list(grays[0.5].shape), shape03=list(grays[0.3].shape), pillow=Image.__version__)
     out['versions'] = dict(numpy=np.__version__, opencv=cv2.__version__,
                            python=sys.version.split()[0], ipp=str(cv2.ipp.getIppVersion()))
     with open(os.path.join(HERE, "versions.json"), "w") as f:
