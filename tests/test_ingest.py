@@ -67,8 +67,9 @@ def test_oracle_ingest_matches_reference_functions():
         assert got.dtype == ref.dtype == np.float32 and np.array_equal(got, ref)
     finally:
         sys.path[:] = saved_path
-        for k in list(sys.modules):
-            if k not in saved:
+        for k in list(sys.modules):                          # drop only the reference's modules and the GUI stubs
+            if k not in saved and k.split(".")[0] in ("FeatureExtractor", "FeatureMatcher", "Runner", "SFM", "PoseEstimator",
+                                                      "Util", "Visualizer", "matplotlib", "mpl_toolkits"):
                 del sys.modules[k]
 
 
