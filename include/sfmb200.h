@@ -21,6 +21,12 @@
  *   sfm_match_ratio_batch    the same method over a list of image pairs (the
  *                            reference loops over consecutive pairs at
  *                            Runner.py:183-191,344-347)
+ *   sfm_matches_to_coords    Runner.py:423-434 (_convert_matches_to_coords)
+ *   sfm_ransac_sample_indices  the np.random.seed(5) / np.random.choice(n, 8,
+ *                            replace=False) draws of SFM.py:45-49,133-137
+ *   sfm_find_inliers         SFM.py:126-160 (CameraPose.find_inliers)
+ *   sfm_ransac_camera_motion SFM.py:38-124 (CameraPose.ransac_camera_motion with
+ *                            _check_valid_pose)
  *
  * Conventions
  *   - Every pointer marked "dev" is CUDA device memory owned by the caller (the
@@ -210,6 +216,61 @@ SFM_EXPORT int sfm_match_ratio_batch(SfmCtx* ctx, void* stream, const float* des
                           const int32_t* pairs_dev, int n_pairs, float ratio_threshold, int mode,
                           void* workspace_dev, size_t workspace_bytes, int32_t* match_out,
                           float* conf_out, int32_t* count_out, int32_t* stats_out, int cap);
+
+/* ---- two-view RANSAC ------------------------ */
+
+/*
+ * Runner.py:423-434 (_convert_matches_to_coords): the first min(count, num_matches) rows of a
+ * match list as two coordinate arrays.  match_dev [*][2] int32 and count_dev [1] int32 are the
+ * matcher's outputs; x1/y1/x2/y2 the extractor's level-0 coordinates of the two images (dev,
+ * int32).  p1_out, p2_out [num_matches][2] float64 (dev); n_out [1] int32 (dev) receives the
+ * number of rows written.
+ */
+SFM_EXPORT int sfm_matches_to_coords(SfmCtx* ctx, void* stream, const int32_t* match_dev, const int32_t* count_dev,
+                                     const int32_t* x1_dev, const int32_t* y1_dev, const int32_t* x2_dev,
+                                     const int32_t* y2_dev, int num_matches, double* p1_out, double* p2_out,
+                                     int32_t* n_out);
+
+/*
+ * HOST function (no device work): the `iterations` 8-subsets that
+ *     np.random.seed(seed); [np.random.choice(n, 8, replace=False) for _ in range(iterations)]
+ * draws (SFM.py:45-49,133-137 with seed 5) -- numpy's legacy MT19937 stream, one Fisher-Yates
+ * permutation of n per draw with masked rejection sampling.  out_host [iterations][8] int32.
+ */
+SFM_EXPORT int sfm_ransac_sample_indices(uint32_t seed, int n, int iterations, int32_t* out_host);
+
+SFM_EXPORT size_t sfm_ransac_workspace_bytes(int iterations);
+
+/*
+ * SFM.py:126-160.  p1_dev, p2_dev [n][2] float64 (dev, n >= 8), samples_dev [iterations][8] int32
+ * (dev).  Outputs (dev): result_out [4] int32 = {winning hypothesis or -1, its inlier count, 0, 0};
+ * inlier_idx_out [n] int32, the winner's inlier rows in ascending order (the reference returns
+ * p1[mask], p2[mask]); f_out [9] float64 (may be NULL), the winner's fundamental matrix.
+ * The winner is the first hypothesis with the largest inlier count, as in the reference.
+ */
+SFM_EXPORT int sfm_find_inliers(SfmCtx* ctx, void* stream, const double* p1_dev, const double* p2_dev, int n,
+                                const int32_t* samples_dev, int iterations, double threshold, void* workspace_dev,
+                                size_t workspace_bytes, int32_t* inlier_idx_out, int32_t* result_out, double* f_out);
+
+/*
+ * SFM.py:38-102 with _check_valid_pose (:104-124).  K1, K2, R_base [9] row-major and T_base [3]
+ * are HOST pointers (copied into the launch).  Outputs as sfm_find_inliers, with result_out[2] =
+ * bit mask of the winner's pose candidates that pass the cheirality test, and pose_out [9 + 48]
+ * float64 (dev) = the winner's F followed by its four candidates (R row-major, T) in the
+ * canonical order (Ra,T), (Ra,-T), (Rb,T), (Rb,-T).  The reference tries the same four in the order
+ * LAPACK's sign choices for svd(E) imply and keeps the first valid one; the Python host layer
+ * re-derives that order from the returned F.
+ */
+SFM_EXPORT int sfm_ransac_camera_motion(SfmCtx* ctx, void* stream, const double* p1_dev, const double* p2_dev, int n,
+                                        const double* K1, const double* K2, const double* R_base, const double* T_base,
+                                        const int32_t* samples_dev, int iterations, double threshold,
+                                        void* workspace_dev, size_t workspace_bytes, int32_t* inlier_idx_out,
+                                        int32_t* result_out, double* pose_out);
+
+/* Device pointers to the per-hypothesis data the last call left in the workspace (parity tests):
+ * F [iterations][9], counts [iterations], valid [iterations], candidates [iterations][48]. */
+SFM_EXPORT int sfm_ransac_debug_views(void* workspace_dev, int iterations, double** f_dev, int32_t** counts_dev,
+                                      uint32_t** valid_dev, double** cand_dev);
 
 #ifdef __cplusplus
 }

@@ -30,6 +30,8 @@ EXPORTS = [
     "sfm_extract_batch", "sfm_extract_status", "sfm_harris_response",
     "sfm_ingest_workspace_bytes", "sfm_ingest_rgb8",
     "sfm_match_workspace_bytes", "sfm_match_ratio", "sfm_match_ratio_batch",
+    "sfm_matches_to_coords", "sfm_ransac_sample_indices", "sfm_ransac_workspace_bytes", "sfm_find_inliers",
+    "sfm_ransac_camera_motion", "sfm_ransac_debug_views",
 ]
 
 
@@ -101,6 +103,14 @@ def load_library() -> C.CDLL:
                                       C.c_size_t, i32p, fp, i32p, C.c_int]
         L.sfm_match_ratio_batch.argtypes = [vp, vp, fp, i32p, C.c_int, C.c_int, i32p, C.c_int, C.c_float,
                                             C.c_int, vp, C.c_size_t, i32p, fp, i32p, i32p, C.c_int]
+        L.sfm_matches_to_coords.argtypes = [vp, vp, i32p, i32p, i32p, i32p, i32p, i32p, C.c_int, vp, vp, i32p]
+        L.sfm_ransac_sample_indices.argtypes = [C.c_uint32, C.c_int, C.c_int, vp]
+        L.sfm_ransac_workspace_bytes.argtypes = [C.c_int]
+        L.sfm_ransac_workspace_bytes.restype = C.c_size_t
+        L.sfm_find_inliers.argtypes = [vp, vp, vp, vp, C.c_int, i32p, C.c_int, C.c_double, vp, C.c_size_t, i32p, i32p, vp]
+        L.sfm_ransac_camera_motion.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, i32p, C.c_int, C.c_double, vp,
+                                               C.c_size_t, i32p, i32p, vp]
+        L.sfm_ransac_debug_views.argtypes = [vp, C.c_int] + [C.POINTER(C.c_void_p)] * 4
         _lib = L
         return L
 

@@ -101,3 +101,26 @@ def synth_descriptors(n: int, image_id: int, base: np.ndarray | None = None,
     src = rng.permutation(base.shape[0])[:npl]
     h[rows] = base[src] + np.abs(rng.normal(0.0, noise, size=(npl, dim)))
     return _rootsift_like(h).astype(np.float32)
+
+
+def two_view_correspondences(n: int, seed: int, outlier_frac: float = 0.3, width: int = 960, height: int = 540,
+                             noise_px: float = 0.4):
+    """Seeded integer-pixel correspondences of a two-view scene for the RANSAC stage (SURVEY.md
+    section 8f row 2): `n` random 3-D points seen by two cameras with the same intrinsics K (a
+    small rotation about y plus a sideways translation), Gaussian pixel noise in the second view,
+    a fraction replaced by uniformly random outliers, coordinates rounded to int64 as the
+    extractor's keypoints are.  Returns (p1 (n,2) int64, p2 (n,2) int64, K (3,3) float64)."""
+    rng = np.random.default_rng(seed)
+    K = np.array([[800.0, 0, width / 2], [0, 800.0, height / 2], [0, 0, 1]])
+    X = np.column_stack([rng.uniform(-4, 4, n), rng.uniform(-2.5, 2.5, n), rng.uniform(4, 12, n)])
+    ang = 0.1
+    R = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]])
+    t = np.array([-1.0, 0.05, 0.1])
+    x1 = (K @ X.T).T
+    x1 = x1[:, :2] / x1[:, 2:]
+    x2 = (K @ (R @ X.T + t[:, None])).T
+    x2 = x2[:, :2] / x2[:, 2:]
+    x2 = x2 + rng.normal(0, noise_px, x2.shape)
+    m = rng.random(n) < outlier_frac
+    x2[m] = np.column_stack([rng.uniform(0, width, int(m.sum())), rng.uniform(0, height, int(m.sum()))])
+    return np.round(x1).astype(np.int64), np.round(x2).astype(np.int64), K
