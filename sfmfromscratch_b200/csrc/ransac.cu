@@ -24,8 +24,11 @@
 // The 8-subsets come from numpy's legacy global generator (np.random.seed(5) followed by
 // np.random.choice(n, 8, replace=False) per iteration): an inherently sequential MT19937 stream
 // with rejection sampling, reproduced on the host by sfm_ransac_sample_indices.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <new>
+#include <shared_mutex>
 
 #include "common.cuh"
 #include "ransac_math.cuh"
@@ -242,30 +245,132 @@ int run_ransac(SfmCtx* ctx, void* stream, const double* p1, const double* p2, in
     return SFM_OK;
 }
 
-// numpy's legacy MT19937 stream (numpy/random/src/mt19937/mt19937.c, distributions.c).
+// numpy's legacy MT19937 stream (numpy/random/src/mt19937/mt19937.c): state + block generation.
 struct Mt19937 {
     uint32_t key[624];
-    int pos;
     explicit Mt19937(uint32_t seed) {
         for (int i = 0; i < 624; ++i) { key[i] = seed; seed = 1812433253u * (seed ^ (seed >> 30)) + (uint32_t)i + 1u; }
-        pos = 624;
     }
-    void refill() {
+    // the next 624 tempered outputs (both loops vectorise: the recurrence reaches 227 elements back)
+    void block(uint32_t* out) {
         constexpr uint32_t UP = 0x80000000u, LO = 0x7fffffffu, MAT = 0x9908b0dfu;
         int i = 0;
-        for (; i < 624 - 397; ++i) { const uint32_t y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i + 397] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u); }
-        for (; i < 623; ++i) { const uint32_t y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i - 227] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u); }
-        const uint32_t y = (key[623] & UP) | (key[0] & LO);
-        key[623] = key[396] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
-        pos = 0;
-    }
-    inline uint32_t next() {
-        if (pos == 624) refill();
-        uint32_t y = key[pos++];
-        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
-        return y;
+        for (; i < 624 - 397; ++i) { const uint32_t y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i + 397] ^ (y >> 1) ^ (MAT & (0u - (y & 1u))); }
+        for (; i < 623; ++i) { const uint32_t y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i - 227] ^ (y >> 1) ^ (MAT & (0u - (y & 1u))); }
+        const uint32_t yl = (key[623] & UP) | (key[0] & LO);
+        key[623] = key[396] ^ (yl >> 1) ^ (MAT & (0u - (yl & 1u)));
+        for (i = 0; i < 624; ++i) {
+            uint32_t y = key[i];
+            y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+            out[i] = y;
+        }
     }
 };
+
+// Source of stream words for the shuffle loop: a window [pos, end) of w, refilled by more().
+struct WordSource {
+    const uint32_t* w = nullptr;
+    size_t pos = 0, end = 0;
+    virtual void more() = 0;
+    virtual ~WordSource() {}
+};
+
+// The stream depends on the seed only, and the reference always seeds with 5 (SFM.py:45,133): the
+// tempered outputs are generated once per process and shared by every call (and every host thread).
+struct StreamCache {
+    std::shared_mutex mu;
+    bool have = false;
+    uint32_t seed = 0;
+    Mt19937 gen{0};
+    std::vector<uint32_t> words;
+    void grow(size_t want) {                               // exclusive lock held
+        const size_t blocks = (want + 623) / 624;
+        if (blocks * 624 <= words.size()) return;
+        const size_t old = words.size();
+        words.resize(blocks * 624);
+        for (size_t o = old; o < words.size(); o += 624) gen.block(words.data() + o);
+    }
+};
+StreamCache g_stream;
+constexpr size_t kCacheMaxWords = (size_t)1 << 28;         // 1 GiB; longer draws stream through a local buffer
+
+struct CachedSource : WordSource {
+    bool locked = false;
+    CachedSource(uint32_t seed, size_t expect) {
+        {
+            std::unique_lock<std::shared_mutex> g(g_stream.mu);
+            if (!g_stream.have || g_stream.seed != seed) {
+                g_stream.have = true; g_stream.seed = seed; g_stream.gen = Mt19937(seed); g_stream.words.clear();
+            }
+            g_stream.grow(expect);
+        }
+        g_stream.mu.lock_shared(); locked = true;
+        w = g_stream.words.data(); end = g_stream.words.size();
+        seed_ = seed;
+    }
+    void more() override {
+        g_stream.mu.unlock_shared(); locked = false;
+        {
+            std::unique_lock<std::shared_mutex> g(g_stream.mu);
+            if (g_stream.seed != seed_) {                   // another thread switched seeds: rebuild up to here
+                g_stream.seed = seed_; g_stream.gen = Mt19937(seed_); g_stream.words.clear();
+            }
+            g_stream.grow(std::max(end + end / 4, end + (size_t)(1 << 20)));
+        }
+        g_stream.mu.lock_shared(); locked = true;
+        w = g_stream.words.data(); end = g_stream.words.size();
+    }
+    ~CachedSource() override { if (locked) g_stream.mu.unlock_shared(); }
+    uint32_t seed_;
+};
+
+struct LocalSource : WordSource {
+    Mt19937 gen;
+    std::vector<uint32_t> buf;
+    explicit LocalSource(uint32_t seed) : gen(seed), buf(624 * 128) { w = buf.data(); }
+    void more() override {
+        for (size_t o = 0; o < buf.size(); o += 624) gen.block(buf.data() + o);
+        pos = 0; end = buf.size();
+    }
+};
+
+// RandomState.choice(n, 8, replace=False) == RandomState.permutation(n)[:8]: a Fisher-Yates shuffle
+// of arange(n), i = n-1 .. 1, with j = random_interval(i) drawn by masked rejection (numpy/random/
+// src/distributions/distributions.c).  Inside one mask level the loop is branch-free: a rejected
+// word swaps perm[i] with itself and leaves i unchanged.
+void legacy_choice8(WordSource& src, int n, int iterations, int32_t* out) {
+    std::vector<int32_t> ident((size_t)n), perm((size_t)n);
+    for (int i = 0; i < n; ++i) ident[i] = i;
+    int32_t* __restrict__ pm = perm.data();
+    for (int it = 0; it < iterations; ++it) {
+        memcpy(pm, ident.data(), (size_t)n * sizeof(int32_t));
+        uint32_t i = (uint32_t)n - 1;
+        while (i >= 1) {
+            uint32_t mask = i;
+            mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+            const uint32_t lo = mask >> 1;                  // this level: lo < i <= mask
+            while (i > lo) {
+                if (src.pos == src.end) src.more();
+                const uint32_t* __restrict__ w = src.w + src.pos;
+                // i - lo words can never take i below lo (each accepts at most one step), so this
+                // many are consumed without testing the level boundary
+                const size_t cnt = std::min<size_t>(src.end - src.pos, (size_t)(i - lo));
+                uint32_t ii = i;
+                for (size_t k = 0; k < cnt; ++k) {
+                    const uint32_t j = w[k] & mask;
+                    const uint32_t acc = j <= ii ? 1u : 0u;
+                    const uint32_t jj = ii ^ ((j ^ ii) & (0u - acc));     // acc ? j : ii without a branch
+                    const int32_t a = pm[ii], b = pm[jj];
+                    pm[ii] = b; pm[jj] = a;
+                    ii -= acc;
+                }
+                i = ii;
+                src.pos += cnt;
+            }
+        }
+        memcpy(out + (size_t)it * 8, pm, 8 * sizeof(int32_t));
+    }
+}
 
 }  // namespace
 
@@ -287,19 +392,24 @@ SFM_EXPORT int sfm_matches_to_coords(SfmCtx* ctx, void* stream, const int32_t* m
 
 SFM_EXPORT int sfm_ransac_sample_indices(uint32_t seed, int n, int iterations, int32_t* out_host) {
     if (!out_host || n < 8 || iterations < 0) return SFM_ERR_BAD_ARG;
-    Mt19937 g(seed);
-    std::vector<int32_t> perm((size_t)n);
-    for (int it = 0; it < iterations; ++it) {
-        for (int i = 0; i < n; ++i) perm[i] = i;
-        uint32_t mask = (uint32_t)(n - 1);                 // smallest 2^k - 1 >= i, tracked as i decreases
+    // expected stream words: sum over the steps of (mask + 1) / (i + 1)
+    double per = 0.0;
+    for (uint32_t i = 1; i < (uint32_t)n; ++i) {
+        uint32_t mask = i;
         mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-        for (uint32_t i = (uint32_t)n - 1; i >= 1; --i) {  // RandomState.shuffle: random_interval(i), swap
-            if (i <= (mask >> 1)) mask >>= 1;
-            uint32_t j;
-            do { j = g.next() & mask; } while (j > i);
-            const int32_t tmp = perm[i]; perm[i] = perm[j]; perm[j] = tmp;
+        per += (double)((uint64_t)mask + 1) / (double)(i + 1);
+    }
+    const double expect = per * iterations * 1.01 + 65536.0;
+    try {
+        if (expect < (double)kCacheMaxWords) {
+            CachedSource src(seed, (size_t)expect);
+            legacy_choice8(src, n, iterations, out_host);
+        } else {
+            LocalSource src(seed);
+            legacy_choice8(src, n, iterations, out_host);
         }
-        memcpy(out_host + (size_t)it * 8, perm.data(), 8 * sizeof(int32_t));
+    } catch (const std::bad_alloc&) {
+        return SFM_ERR_UNSUPPORTED;
     }
     return SFM_OK;
 }
