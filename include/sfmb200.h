@@ -24,6 +24,10 @@
  *   sfm_matches_to_coords    Runner.py:423-434 (_convert_matches_to_coords)
  *   sfm_ransac_sample_indices  the np.random.seed(5) / np.random.choice(n, 8,
  *                            replace=False) draws of SFM.py:45-49,133-137
+ *   sfm_associate_nearest    Runner.py:241-247 (nearest already-triangulated 2-D point of
+ *                            every previous-frame match, SFM.py:376-382 distances)
+ *   sfm_dedup_points         Runner.py:361-385 (add_points / is_new_point /
+ *                            find_existing_point)
  *   sfm_find_inliers         SFM.py:126-160 (CameraPose.find_inliers)
  *   sfm_ransac_camera_motion SFM.py:38-124 (CameraPose.ransac_camera_motion with
  *                            _check_valid_pose)
@@ -271,6 +275,33 @@ SFM_EXPORT int sfm_ransac_camera_motion(SfmCtx* ctx, void* stream, const double*
  * F [iterations][9], counts [iterations], valid [iterations], candidates [iterations][48]. */
 SFM_EXPORT int sfm_ransac_debug_views(void* workspace_dev, int iterations, double** f_dev, int32_t** counts_dev,
                                       uint32_t** valid_dev, double** cand_dev);
+
+/* ---- point association ----------------------- */
+
+/*
+ * Runner.py:241-247.  ref_dev [m][2], query_dev [q][2] float64 (dev).  For every query row:
+ * nearest_out [q] int32 = np.argmin of its distances to the ref rows (first minimum), dist_out [q]
+ * float64 (may be NULL) that distance, flag_out [q] int32 = distance < dist_threshold; kept_out [q]
+ * int32 = the flagged query rows in ascending order, count_out [1] their number.
+ */
+SFM_EXPORT int sfm_associate_nearest(SfmCtx* ctx, void* stream, const double* ref_dev, int m, const double* query_dev,
+                                     int q, double dist_threshold, int32_t* nearest_out, double* dist_out,
+                                     int32_t* flag_out, int32_t* kept_out, int32_t* count_out);
+
+/*
+ * Runner.py:361-385 for one batch: pts_dev [n][3] float64 are visited in order against the global
+ * store store_dev [e][3] (e may be 0).  A point with no stored point closer than `threshold`
+ * (existing, or an earlier new point of the batch) is new and takes the next store slot; any other
+ * maps to the first nearest stored point.  Outputs (dev): index_out [n] int32 store index per point
+ * (new points: e, e+1, ... in batch order), is_new_out [n] int32, n_new_out [1] int32.
+ * pair_cap bounds the number of (earlier point, point) pairs closer than the threshold that the
+ * workspace can list (duplicates inside a batch are rare: n is a safe default); if it is exceeded
+ * n_new_out is set to -1 and index_out[0] to the capacity needed, and the caller repeats the call.
+ */
+SFM_EXPORT size_t sfm_dedup_workspace_bytes(int n, int pair_cap);
+SFM_EXPORT int sfm_dedup_points(SfmCtx* ctx, void* stream, const double* pts_dev, int n, const double* store_dev, int e,
+                                double threshold, int pair_cap, void* workspace_dev, size_t workspace_bytes,
+                                int32_t* index_out, int32_t* is_new_out, int32_t* n_new_out);
 
 #ifdef __cplusplus
 }

@@ -32,6 +32,7 @@ EXPORTS = [
     "sfm_match_workspace_bytes", "sfm_match_ratio", "sfm_match_ratio_batch",
     "sfm_matches_to_coords", "sfm_ransac_sample_indices", "sfm_ransac_workspace_bytes", "sfm_find_inliers",
     "sfm_ransac_camera_motion", "sfm_ransac_debug_views",
+    "sfm_associate_nearest", "sfm_dedup_workspace_bytes", "sfm_dedup_points",
 ]
 
 
@@ -111,6 +112,10 @@ def load_library() -> C.CDLL:
         L.sfm_ransac_camera_motion.argtypes = [vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, i32p, C.c_int, C.c_double, vp,
                                                C.c_size_t, i32p, i32p, vp]
         L.sfm_ransac_debug_views.argtypes = [vp, C.c_int] + [C.POINTER(C.c_void_p)] * 4
+        L.sfm_associate_nearest.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.c_double, i32p, vp, i32p, i32p, i32p]
+        L.sfm_dedup_workspace_bytes.argtypes = [C.c_int, C.c_int]
+        L.sfm_dedup_workspace_bytes.restype = C.c_size_t
+        L.sfm_dedup_points.argtypes = [vp, vp, vp, C.c_int, vp, C.c_int, C.c_double, C.c_int, vp, C.c_size_t, i32p, i32p, i32p]
         _lib = L
         return L
 

@@ -62,3 +62,70 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+# ---------------------------------------------------------------- association (section 8f row 3)
+
+def _runner_module():
+    """Runner.py imports matplotlib (absent here) for its plots: stub the GUI modules."""
+    import importlib.util
+    import types
+
+    class _Stub(types.ModuleType):
+        def __getattr__(self, name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            return type(name, (), {"__init__": lambda self, *a, **k: None, "__call__": lambda self, *a, **k: None})
+    for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.widgets", "matplotlib.cm", "matplotlib.colors",
+                 "mpl_toolkits", "mpl_toolkits.mplot3d"):
+        if name not in sys.modules:
+            m = _Stub(name)
+            m.__path__ = []
+            sys.modules[name] = m
+    spec = importlib.util.spec_from_file_location("Runner", os.path.join(REF, "Runner.py"))
+    R = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(R)
+    return R
+
+
+def assoc_main():
+    import types
+    R = _runner_module()
+    out = {}
+    rng = np.random.default_rng(7)
+    # Runner.py:241-247 replayed with the reference's own distance helper
+    for k, (m, q, thr) in enumerate([(400, 300, 5.0), (50, 80, 2.0), (1, 5, 5.0)]):
+        prev = rng.integers(0, 960, (m, 2)).astype(np.int64)
+        qry = prev[rng.integers(0, m, q)] + rng.integers(-6, 7, (q, 2))
+        if m > 10:
+            prev[5] = prev[3]                                   # duplicated triangulated point: first index wins
+        rows, near = [], []
+        for p_prime in range(qry.shape[0]):
+            dist = CameraPose.compute_euclidean_distance(prev, qry[p_prime:p_prime + 1])
+            mask = np.argmin(dist)
+            if dist[mask] < thr:
+                rows.append(p_prime)
+                near.append(mask)
+        out.update({f"assoc{k}_prev": prev, f"assoc{k}_query": qry, f"assoc{k}_thr": thr,
+                    f"assoc{k}_rows": np.array(rows, np.int64), f"assoc{k}_near": np.array(near, np.int64)})
+    # Runner.py:361-385: SFMRunner.add_points on a bare object carrying the attributes it touches
+    for k, (n1, n2) in enumerate([(120, 90), (40, 60)]):
+        self = types.SimpleNamespace(global_points_3D=[], global_points_2D=[], frame_indices=[], point_indices=[])
+        for name in ("is_new_point", "find_existing_point", "add_points"):
+            setattr(self, name, types.MethodType(getattr(R.SFMRunner, name), self))
+        a = rng.normal(size=(n1, 3)) * 5
+        a[10] = a[2]; a[11] = a[2] + 3e-7; a[30] = a[29] + 9e-7   # duplicates inside the first batch
+        b = rng.normal(size=(n2, 3)) * 5
+        b[::3] = a[rng.integers(0, n1, len(b[::3]))]              # re-observed points in the second batch
+        b[1] = b[0] + 5e-7
+        self.add_points(a, rng.integers(0, 900, (n1, 2)), 0)
+        first = len(self.point_indices)
+        self.add_points(b, rng.integers(0, 900, (n2, 2)), 1)
+        out.update({f"dedup{k}_a": a, f"dedup{k}_b": b, f"dedup{k}_idx_a": np.array(self.point_indices[:first]),
+                    f"dedup{k}_idx_b": np.array(self.point_indices[first:]), f"dedup{k}_store": np.array(self.global_points_3D)})
+    np.savez_compressed(os.path.join(HERE, "geometry_assoc.npz"), **out)
+    print("wrote geometry_assoc.npz:", {k: np.asarray(v).shape for k, v in out.items() if "idx" in k or "rows" in k})
+
+
+if __name__ == "__main__":
+    assoc_main()
