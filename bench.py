@@ -172,6 +172,104 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------- SURVEY 8f rows 2-3
+
+def geometry_leg(torch, N, local, cpu=True):
+    """Two-view RANSAC (Runner.py:170,351: 5 967 hypotheses per pair) over 16 synthetic match sets of
+    600..2500 correspondences, and the association scans, each timed (a) on the device with inputs
+    and 8-subsets resident, (b) through the reference-facing call with numpy in/out, which includes
+    the host replay of numpy's MT19937 stream that draws the subsets."""
+    from sfmfromscratch_b200 import association as AS
+    from sfmfromscratch_b200 import geometry as GE
+    from sfmfromscratch_b200.synth import two_view_correspondences
+    it = GE.calculate_num_ransac_iterations(0.98, 8, 0.4)
+    sizes = [int(v) for v in np.linspace(600, 2500, 16)]
+    pairs = [two_view_correspondences(n, 100 + k, 0.4)[:2] for k, n in enumerate(sizes)]
+    dev_pairs = [(torch.from_numpy(a.astype(np.float64)).cuda(), torch.from_numpy(b.astype(np.float64)).cuda()) for a, b in pairs]
+    t0 = time.perf_counter()
+    samples = [GE._samples_host(n, it, GE.RANSAC_SEED) for n in sizes]
+    sampler_first_ms = (time.perf_counter() - t0) * 1e3
+    dev_samples = [s.cuda() for s in samples]
+
+    def resident():
+        for (a, b), s in zip(dev_pairs, dev_samples):
+            GE.ransac_device(a, b, it, samples=s)
+    for _ in range(3):
+        resident()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    N.profile_enable(True, local)
+    e0.record()
+    for _ in range(reps):
+        resident()
+    e1.record()
+    torch.cuda.synchronize()
+    kst = N.profile_collect(local)
+    N.profile_enable(False, local)
+    res_ms = e0.elapsed_time(e1) / reps
+    evals = float(sum(sizes)) * it
+
+    def host_call(threads):
+        GE._samples_host.cache_clear()                     # every pair of a real run has its own size
+        t = time.perf_counter()
+        out = GE.find_inliers_many(pairs, max_iterations=it, threads=threads)
+        return (time.perf_counter() - t) * 1e3, out
+    host_call(8)
+    ms1, _ = host_call(1)
+    ms8, out8 = host_call(8)
+    GE._samples_host.cache_clear()
+    t0 = time.perf_counter()
+    for n in sizes:
+        GE._samples_host(n, it, GE.RANSAC_SEED)
+    sampler_ms = (time.perf_counter() - t0) * 1e3
+
+    # association: 2500 previous-frame matches against 2500 triangulated points; 2500 new 3-D points
+    # against a store of 100 000
+    rng = np.random.default_rng(0)
+    prev = torch.from_numpy(rng.integers(0, 1920, (2500, 2)).astype(np.float64)).cuda()
+    qry = torch.from_numpy(rng.integers(0, 1920, (2500, 2)).astype(np.float64)).cuda()
+    store = torch.from_numpy(rng.normal(size=(100000, 3))).cuda()
+    batch = torch.cat([store[torch.from_numpy(rng.integers(0, 100000, 1250)).cuda()], torch.from_numpy(rng.normal(size=(1250, 3))).cuda()])
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+    assoc_ms = timed(lambda: AS.associate_device(prev, qry, 5.0))
+    dedup_ms = timed(lambda: AS.dedup_device(batch, store))
+
+    cpu_leg = None
+    if cpu:
+        from oracle import geometry as OG
+        a, b = pairs[len(pairs) // 2]
+        it_cpu = 300
+        t0 = time.perf_counter()
+        OG.find_inliers(a, b, max_iterations=it_cpu)
+        dt = time.perf_counter() - t0
+        cpu_leg = {"value": it_cpu * len(a) / dt, "unit": "hypothesis-correspondence evaluations/s", "cores": 1, "kind": "port",
+                   "seconds": dt, "sample": f"{it_cpu} of the {it} hypotheses of one pair of {len(a)} correspondences through the "
+                                            f"oracle (numpy/LAPACK restatement of SFM.py:126-160, bit-identical to the reference here)"}
+    return {"workload": f"CameraPose.find_inliers, {it} hypotheses per pair, 16 pairs of 600..2500 correspondences (40% outliers)",
+            "resident": {"ms_per_pair": res_ms / len(sizes), "pairs_per_s": len(sizes) / (res_ms * 1e-3),
+                         "hypothesis_correspondence_evals_per_s": evals / (res_ms * 1e-3),
+                         "kernels_ms_per_pair": {k: v[1] / reps / len(sizes) for k, v in sorted(kst.items())}},
+            "host_call": {"ms_per_pair_1_thread": ms1 / len(sizes), "ms_per_pair_8_threads": ms8 / len(sizes),
+                          "pairs_per_s_8_threads": len(sizes) / (ms8 * 1e-3),
+                          "sampler_ms_per_pair_1_thread": sampler_ms / len(sizes), "sampler_first_call_ms": sampler_first_ms,
+                          "inliers": [int(len(o[0])) for o in out8],
+                          "note": "numpy arrays in, inlier arrays out; the time is the host replay of np.random.seed(5) / "
+                                  "np.random.choice(n, 8, replace=False) (sequential MT19937 + rejection, ~1.5 ns per stream word)"},
+            "association": {"associate_2500x2500_ms": assoc_ms, "dedup_2500_vs_100000_ms": dedup_ms},
+            "cpu_baseline": cpu_leg}
+
+
 # ---------------------------------------------------------------------------- GPU arm
 
 def run_ours(args):
@@ -419,6 +517,11 @@ def run_ours(args):
                 "note": "wall clock incl. the host read of the keypoint counts between extraction and matching"}
         del keep4
 
+    # ---- two-view RANSAC and point association on the matcher's output
+    geom = None
+    if rank == 0 and not args.no_geometry:
+        geom = geometry_leg(torch, N, local, cpu=(world == 1 and not args.no_cpu))
+
     # ---- CPU baseline on a bounded sample (rank 0, N == 1 only)
     cpu = None
     if world == 1 and rank == 0 and not args.no_cpu:
@@ -439,7 +542,7 @@ def run_ours(args):
                            "parallelism": f"image shards x{world}, descriptor all-gather (NCCL), pair shards"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": sampler.summary(), "ms_per_step_profiled": prof_ms, "kernels": kernels, "match": match,
-                "single_image": single, "config2_4k_pair": cfg2}
+                "single_image": single, "config2_4k_pair": cfg2, "geometry": geom}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -454,6 +557,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-4k", action="store_true", help="skip the configs[2] leg")
+    ap.add_argument("--no-geometry", action="store_true", help="skip the RANSAC / association leg (SURVEY 8f rows 2-3)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

@@ -181,3 +181,30 @@ class CameraPose:
         cand = best[9 + 12 * c: 9 + 12 * (c + 1)]
         keep = idx[:int(res[1])].cpu().numpy()
         return cand[:9].reshape(3, 3).copy(), cand[9:].copy(), p1[keep], p2[keep]
+
+
+def find_inliers_many(pairs, threshold: float = 1.0, max_iterations: int = 1000, threads: int = 8):
+    """`CameraPose.find_inliers` over a list of (p1, p2) pairs -- what the reference's 8-thread pool
+    does pair by pair (Runner.py:186-191,351).  The 8-subsets of every pair are drawn concurrently on
+    `threads` host threads (the draw is the sequential MT19937 replay; ctypes releases the GIL), the
+    hypothesis kernels of all pairs queue on the current stream, and results are read back once.
+    Returns a list with the reference's per-pair return values."""
+    from concurrent.futures import ThreadPoolExecutor
+    pairs = [(np.asarray(a), np.asarray(b)) for a, b in pairs]
+    todo = [k for k, (a, _) in enumerate(pairs) if len(a) >= 8 and max_iterations >= 1]
+    out = [(None, None, None, None) if len(a) < 8 else (np.array([]), np.array([])) for a, _ in pairs]
+    if not todo:
+        return out
+    with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+        samples = list(ex.map(lambda k: _samples_host(len(pairs[k][0]), int(max_iterations), RANSAC_SEED), todo))
+    res = []
+    for k, s in zip(todo, samples):
+        a, b = pairs[k]
+        res.append(ransac_device(_upload(a), _upload(b), max_iterations, threshold, samples=s.to('cuda', non_blocking=True)))
+    torch.cuda.synchronize()
+    for k, (idx, r, _) in zip(todo, res):
+        r = r.cpu().numpy()
+        if r[0] >= 0:
+            keep = idx[:int(r[1])].cpu().numpy()
+            out[k] = (pairs[k][0][keep], pairs[k][1][keep])
+    return out
