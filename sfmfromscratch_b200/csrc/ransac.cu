@@ -28,7 +28,9 @@
 #include <cmath>
 #include <cstring>
 #include <new>
-#include <shared_mutex>
+#include <memory>
+#include <mutex>
+#include <utility>
 
 #include "common.cuh"
 #include "ransac_math.cuh"
@@ -276,52 +278,54 @@ struct WordSource {
 };
 
 // The stream depends on the seed only, and the reference always seeds with 5 (SFM.py:45,133): the
-// tempered outputs are generated once per process and shared by every call (and every host thread).
+// tempered outputs are generated once per process and shared by every call and host thread.  The
+// buffer's address space is reserved once (pages are committed as they are written), so growing it
+// never moves the words concurrent readers are walking over.
 struct StreamCache {
-    std::shared_mutex mu;
-    bool have = false;
-    uint32_t seed = 0;
-    Mt19937 gen{0};
+    explicit StreamCache(uint32_t seed) : gen(seed) {}
+    std::mutex grow_mu;
+    Mt19937 gen;
     std::vector<uint32_t> words;
-    void grow(size_t want) {                               // exclusive lock held
-        const size_t blocks = (want + 623) / 624;
-        if (blocks * 624 <= words.size()) return;
+    std::atomic<size_t> ready{0};
+    void grow(size_t want) {
+        std::lock_guard<std::mutex> g(grow_mu);
+        want = std::min(((want + 623) / 624) * 624, words.capacity() / 624 * 624);
         const size_t old = words.size();
-        words.resize(blocks * 624);
-        for (size_t o = old; o < words.size(); o += 624) gen.block(words.data() + o);
+        if (want <= old) return;
+        words.resize(want);                                 // within the reserved capacity: no reallocation
+        for (size_t o = old; o < want; o += 624) gen.block(words.data() + o);
+        ready.store(want, std::memory_order_release);
     }
 };
-StreamCache g_stream;
-constexpr size_t kCacheMaxWords = (size_t)1 << 28;         // 1 GiB; longer draws stream through a local buffer
+constexpr size_t kCacheMaxWords = (size_t)1 << 28;         // 1 GiB of address space; longer draws stream locally
+std::mutex g_caches_mu;
+std::vector<std::pair<uint32_t, std::shared_ptr<StreamCache>>> g_caches;
+
+std::shared_ptr<StreamCache> stream_cache(uint32_t seed) {
+    std::lock_guard<std::mutex> g(g_caches_mu);
+    for (auto& c : g_caches) if (c.first == seed) return c.second;
+    auto c = std::make_shared<StreamCache>(seed);
+    c->words.reserve(kCacheMaxWords);                       // may throw bad_alloc: caller streams locally instead
+    if (g_caches.size() >= 4) g_caches.erase(g_caches.begin());
+    g_caches.emplace_back(seed, c);
+    return c;
+}
 
 struct CachedSource : WordSource {
-    bool locked = false;
-    CachedSource(uint32_t seed, size_t expect) {
-        {
-            std::unique_lock<std::shared_mutex> g(g_stream.mu);
-            if (!g_stream.have || g_stream.seed != seed) {
-                g_stream.have = true; g_stream.seed = seed; g_stream.gen = Mt19937(seed); g_stream.words.clear();
-            }
-            g_stream.grow(expect);
-        }
-        g_stream.mu.lock_shared(); locked = true;
-        w = g_stream.words.data(); end = g_stream.words.size();
-        seed_ = seed;
+    std::shared_ptr<StreamCache> c;
+    CachedSource(uint32_t seed, size_t expect) : c(stream_cache(seed)) {
+        c->grow(expect);
+        w = c->words.data();
+        end = c->ready.load(std::memory_order_acquire);
     }
     void more() override {
-        g_stream.mu.unlock_shared(); locked = false;
-        {
-            std::unique_lock<std::shared_mutex> g(g_stream.mu);
-            if (g_stream.seed != seed_) {                   // another thread switched seeds: rebuild up to here
-                g_stream.seed = seed_; g_stream.gen = Mt19937(seed_); g_stream.words.clear();
-            }
-            g_stream.grow(std::max(end + end / 4, end + (size_t)(1 << 20)));
+        const size_t have = c->ready.load(std::memory_order_acquire);
+        if (have <= end) {
+            c->grow(std::max(end + end / 4, end + (size_t)(1 << 20)));
+            if (c->ready.load(std::memory_order_acquire) <= end) throw std::bad_alloc();   // reservation exhausted
         }
-        g_stream.mu.lock_shared(); locked = true;
-        w = g_stream.words.data(); end = g_stream.words.size();
+        end = c->ready.load(std::memory_order_acquire);
     }
-    ~CachedSource() override { if (locked) g_stream.mu.unlock_shared(); }
-    uint32_t seed_;
 };
 
 struct LocalSource : WordSource {
@@ -336,8 +340,7 @@ struct LocalSource : WordSource {
 
 // RandomState.choice(n, 8, replace=False) == RandomState.permutation(n)[:8]: a Fisher-Yates shuffle
 // of arange(n), i = n-1 .. 1, with j = random_interval(i) drawn by masked rejection (numpy/random/
-// src/distributions/distributions.c).  Inside one mask level the loop is branch-free: a rejected
-// word swaps perm[i] with itself and leaves i unchanged.
+// src/distributions/distributions.c).
 void legacy_choice8(WordSource& src, int n, int iterations, int32_t* out) {
     std::vector<int32_t> ident((size_t)n), perm((size_t)n);
     for (int i = 0; i < n; ++i) ident[i] = i;
@@ -352,19 +355,24 @@ void legacy_choice8(WordSource& src, int n, int iterations, int32_t* out) {
             while (i > lo) {
                 if (src.pos == src.end) src.more();
                 const uint32_t* __restrict__ w = src.w + src.pos;
-                // i - lo words can never take i below lo (each accepts at most one step), so this
-                // many are consumed without testing the level boundary
-                const size_t cnt = std::min<size_t>(src.end - src.pos, (size_t)(i - lo));
-                uint32_t ii = i;
-                for (size_t k = 0; k < cnt; ++k) {
+                // Two phases per chunk (keeps the stream scan free of the permutation's loads and
+                // stores).  Phase 1: i - lo words can never take i below lo (each accepts at most one
+                // step), so that many are scanned without testing the level boundary; word k is
+                // accepted iff its value is <= i - (accepted so far).  Phase 2: the swaps.
+                const uint32_t cnt = (uint32_t)std::min<size_t>(std::min<size_t>(src.end - src.pos, (size_t)(i - lo)), 512);
+                uint32_t js[512];
+                uint32_t c = 0;
+                for (uint32_t k = 0; k < cnt; ++k) {
                     const uint32_t j = w[k] & mask;
-                    const uint32_t acc = j <= ii ? 1u : 0u;
-                    const uint32_t jj = ii ^ ((j ^ ii) & (0u - acc));     // acc ? j : ii without a branch
-                    const int32_t a = pm[ii], b = pm[jj];
-                    pm[ii] = b; pm[jj] = a;
-                    ii -= acc;
+                    js[c] = j;
+                    c += (j <= i - c) ? 1u : 0u;
                 }
-                i = ii;
+                for (uint32_t q = 0; q < c; ++q) {
+                    const uint32_t jj = js[q];
+                    const int32_t a = pm[i], b = pm[jj];
+                    pm[i] = b; pm[jj] = a;
+                    --i;
+                }
                 src.pos += cnt;
             }
         }
@@ -400,16 +408,21 @@ SFM_EXPORT int sfm_ransac_sample_indices(uint32_t seed, int n, int iterations, i
         per += (double)((uint64_t)mask + 1) / (double)(i + 1);
     }
     const double expect = per * iterations * 1.01 + 65536.0;
-    try {
-        if (expect < (double)kCacheMaxWords) {
+    bool done = false;
+    if (expect < (double)kCacheMaxWords * 0.9) {
+        try {
             CachedSource src(seed, (size_t)expect);
             legacy_choice8(src, n, iterations, out_host);
-        } else {
+            done = true;
+        } catch (const std::bad_alloc&) {}                  // no address space for the shared cache: stream locally
+    }
+    if (!done) {
+        try {
             LocalSource src(seed);
             legacy_choice8(src, n, iterations, out_host);
+        } catch (const std::bad_alloc&) {
+            return SFM_ERR_UNSUPPORTED;
         }
-    } catch (const std::bad_alloc&) {
-        return SFM_ERR_UNSUPPORTED;
     }
     return SFM_OK;
 }
