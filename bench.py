@@ -394,12 +394,17 @@ def run_ours(args):
 
     e2e_steps = max(3, min(args.steps, 30))
     e2e_ms = timed(e2e_step, e2e_steps, min(args.warmup, 3)) / e2e_steps
+    # the PCIe floor of that step: the same pinned host batch copied to the device with nothing else running
+    scratch = torch.empty_like(images)
+    h2d_ms = timed(lambda: scratch.copy_(host_batch, non_blocking=True), 10, 2) / 10
+    del scratch
     h2d = host_batch.numel() * 4
     d2h = (h_x.numel() + h_y.numel() + h_d.numel() + h_c.numel()) * 4
     if n_my_pairs:
         d2h += (h_m.numel() + h_mc.numel() + h_mn.numel()) * 4
     e2e = {"value": pixels_per_step / (e2e_ms * 1e-3) / 1e6, "unit": "Mpixel/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "h2d_copy_alone_ms": h2d_ms, "h2d_copy_alone_gb_per_s": host_batch.numel() * 4 / (h2d_ms * 1e-3) / 1e9,
            "api": "FeaturePipeline.run_host: pinned host images in, pinned host keypoints/descriptors/matches out; "
                   "chunks of 8 images, H2D / kernels / D2H overlapped on three streams"}
 
