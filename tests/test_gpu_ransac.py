@@ -172,3 +172,36 @@ def test_matches_to_coords_device(geo):
             assert np.array_equal(p1[:k].cpu().numpy(), a) and np.array_equal(p2[:k].cpu().numpy(), b)
         ah, bh = geo.convert_matches_to_coords(m[:count], X1, Y1, X2, Y2, num)
         assert np.array_equal(ah, a) and np.array_equal(bh, b)
+
+
+def test_config0_two_view_chain(geo):
+    """BASELINE configs[0]: a synthetic 640x480 pair through the reference-facing classes -- extraction,
+    NN-ratio matching, match -> coordinate conversion and find_inliers with the reference's 5 967
+    iterations (Runner.py:334-351) -- against the oracle running the same chain on the CPU.  Keypoints
+    are identical; the oracle matches the GPU's descriptors (its own differ by an ulp), so every later
+    stage must agree exactly."""
+    from oracle import oracle as O
+    from sfmfromscratch_b200 import NNRatioFeatureMatcher, ScaleRotInvSIFT
+    from sfmfromscratch_b200.synth import second_view, synth_image
+    a = synth_image(480, 640, 0)
+    b = second_view(a, 1)
+    ga, gb = ScaleRotInvSIFT(a, {}), ScaleRotInvSIFT(b, {})
+    oa, ob = O.ScaleRotInvSIFT(a, {}), O.ScaleRotInvSIFT(b, {})
+    (x1, y1), (x2, y2) = ga.detect_keypoints(), gb.detect_keypoints()
+    assert np.array_equal(x1, oa.detect_keypoints()[0]) and np.array_equal(y2, ob.detect_keypoints()[1])
+    f1, f2 = ga.extract_descriptors(), gb.extract_descriptors()
+    m, c = NNRatioFeatureMatcher(0.8).match_features_ratio_test(f1, f2)
+    mo, co = O.NNRatioFeatureMatcher(0.8).match_features_ratio_test(f1, f2)
+    assert np.array_equal(m, mo) and np.array_equal(c, co)
+    p1, p2 = geo.convert_matches_to_coords(m, x1, y1, x2, y2, 2500)
+    q1, q2 = G.convert_matches_to_coords(mo, x1, y1, x2, y2, 2500)
+    assert np.array_equal(p1, q1) and np.array_equal(p2, q2) and p1.dtype == np.int64
+    it = geo.CameraPose.calculate_num_ransac_iterations(0.98, 8, 0.4)
+    i1, i2 = geo.CameraPose.find_inliers(p1, p2, max_iterations=it)
+    o1, o2 = G.find_inliers(q1, q2, max_iterations=it)
+    assert np.array_equal(i1, o1) and np.array_equal(i2, o2)
+    assert len(i1) > 0.5 * len(p1)                       # the affine second view is one rigid motion
+    many = geo.find_inliers_many([(p1, p2), (p1[:7], p2[:7]), (p1[:100], p2[:100])], max_iterations=it, threads=2)
+    assert np.array_equal(many[0][0], o1) and many[1] == (None, None, None, None)
+    o100 = G.find_inliers(q1[:100], q2[:100], max_iterations=it)
+    assert np.array_equal(many[2][0], o100[0]) and np.array_equal(many[2][1], o100[1])
