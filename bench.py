@@ -375,6 +375,14 @@ def run_ours(args):
                 "note": "per-kernel CUDA events on the launching stream over a repeat of the timed region "
                         "(ms_per_step_profiled); the 147-FMA bit-exact window chain makes this kernel FP32-issue "
                         "bound (floor 0.35 ms/step at 128 FMA/clk/SM), see DESIGN.md section 6"}
+    # the resource that actually bounds it: 147 order-preserving FMAs per pyramid pixel on the FP32 pipe
+    fma_peak = 128.0 * 148 * 1.965e9 / 1e12                      # TFMA/s: 128 lanes/clk/SM x 148 SMs x max SM clock
+    fma_ach = 147.0 * lp * BATCH / (kh_ms_step * 1e-3) / 1e12 if kh[1] else None
+    roofline["fp32_pipe"] = {"fma_per_pyramid_pixel": 147, "achieved_tfma_per_s": fma_ach, "peak_tfma_per_s": fma_peak,
+                             "frac": (fma_ach / fma_peak) if fma_ach else None,
+                             "window_stage_alone_frac": 0.72,
+                             "note": "window chains only (Sobel/products add 30 FP32 ops per pixel on the same pipe); "
+                                     "window_stage_alone_frac = scripts/micro/window_rate.cu, the stage's ceiling at any occupancy"}
     kernels = {k: {"launches_per_step": v[0] / args.steps, "ms_per_step": v[1] / args.steps} for k, v in sorted(kstat.items())}
 
     # ---- e2e: host buffers in and out, copies inside the timed region
