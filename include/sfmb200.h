@@ -251,6 +251,11 @@ SFM_EXPORT size_t sfm_ransac_workspace_bytes(int iterations);
  * inlier_idx_out [n] int32, the winner's inlier rows in ascending order (the reference returns
  * p1[mask], p2[mask]); f_out [9] float64 (may be NULL), the winner's fundamental matrix.
  * The winner is the first hypothesis with the largest inlier count, as in the reference.
+ * A sample is degenerate when its 8x9 design matrix is numerically rank-deficient (|R| diagonal of its QR
+ * spanning more than 1e10): the null space then has several dimensions and the vector LAPACK returns --
+ * hence the reference's F, inlier count and possibly its winner -- is decided by rounding noise.  With
+ * result_out[3] == 0 the outputs are the reference's; otherwise they are one valid outcome of the same
+ * procedure (typical cause: a pair without relative motion, p1 == p2 up to a shift).
  */
 SFM_EXPORT int sfm_find_inliers(SfmCtx* ctx, void* stream, const double* p1_dev, const double* p2_dev, int n,
                                 const int32_t* samples_dev, int iterations, double threshold, void* workspace_dev,

@@ -45,10 +45,10 @@ struct RansacPlan {
     double thr;
     double* F;                // [iters][9]
     int32_t* counts;          // [iters]
-    uint32_t* valid;          // [iters], bit c = candidate c passes the cheirality test (pose mode)
+    uint32_t* valid;          // [iters], bit c = candidate c passes the cheirality test (pose mode); bit 31 = degenerate sample
     double* cand;             // [iters][4][12]: R row-major, T (pose mode)
     double K1[9], K2[9], Rb[9], Tb[3], P1[12];
-    int32_t* result;          // [4]: winner (-1: none), its inlier count, its valid bits, 0
+    int32_t* result;          // [4]: winner (-1: none), its inlier count, its valid bits, number of degenerate samples
     int32_t* inliers;         // [n]
     double* best;             // [9 + 48]: winner's F and candidates (may be null)
 };
@@ -64,9 +64,11 @@ __global__ void __launch_bounds__(64) k_ransac_fit(const __grid_constant__ Ransa
         x1[j] = a.x; y1[j] = a.y; x2[j] = b.x; y2[j] = b.y;
     }
     double F[9];
-    fundamental_8pt(x1, y1, x2, y2, F);
+    bool degenerate;
+    fundamental_8pt(x1, y1, x2, y2, F, &degenerate);
 #pragma unroll
     for (int i = 0; i < 9; ++i) P.F[(size_t)it * 9 + i] = F[i];
+    P.valid[it] = degenerate ? 0x80000000u : 0u;
     if (P.pose) {
         double cand[48];
         pose_candidates(F, P.K1, P.K2, cand);
@@ -100,7 +102,7 @@ __global__ void __launch_bounds__(128) k_ransac_valid(const __grid_constant__ Ra
 __global__ void __launch_bounds__(256) k_ransac_score(const __grid_constant__ RansacPlan P) {
     const int it = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (it >= P.iters) return;
-    if (P.pose && P.valid[it] == 0) { if (lane == 0) P.counts[it] = 0; return; }
+    if (P.pose && (P.valid[it] & 0xfu) == 0) { if (lane == 0) P.counts[it] = 0; return; }
     double F[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) F[i] = P.F[(size_t)it * 9 + i];
@@ -119,9 +121,12 @@ __global__ void __launch_bounds__(1024) k_ransac_select(const __grid_constant__ 
     // key: count descending, then iteration ascending; a hypothesis needs at least one inlier
     // (and, in pose mode, one valid candidate) to replace the reference's empty initial best
     unsigned long long best = 0ull;
+    int n_deg = 0;
     for (int it = t; it < P.iters; it += 1024) {
         const int c = P.counts[it];
-        if (c > 0 && (!P.pose || P.valid[it] != 0)) {
+        const uint32_t v = P.valid[it];
+        n_deg += (int)(v >> 31);
+        if (c > 0 && (!P.pose || (v & 0xfu) != 0)) {
             const unsigned long long key = ((unsigned long long)(uint32_t)c << 32) | (uint32_t)(0x7fffffff - it);
             best = key > best ? key : best;
         }
@@ -130,8 +135,11 @@ __global__ void __launch_bounds__(1024) k_ransac_select(const __grid_constant__ 
         const unsigned long long v = __shfl_xor_sync(0xffffffffu, best, o);
         best = v > best ? v : best;
     }
+    n_deg = __reduce_add_sync(0xffffffffu, n_deg);
+    if (t == 0) s_total = 0;
     if (lane == 0) s_best[warp] = best;
     __syncthreads();
+    if (lane == 0 && n_deg) atomicAdd(&s_total, n_deg);
     if (warp == 0) {
         best = s_best[lane];
         for (int o = 16; o; o >>= 1) {
@@ -142,8 +150,9 @@ __global__ void __launch_bounds__(1024) k_ransac_select(const __grid_constant__ 
     }
     __syncthreads();
     best = s_best[0];
+    n_deg = s_total;
     if (best == 0ull) {
-        if (t < 4) P.result[t] = (t == 0) ? -1 : 0;
+        if (t < 4) P.result[t] = (t == 0) ? -1 : (t == 3 ? n_deg : 0);
         return;
     }
     const int win = 0x7fffffff - (int)(uint32_t)(best & 0xffffffffull);
@@ -153,8 +162,8 @@ __global__ void __launch_bounds__(1024) k_ransac_select(const __grid_constant__ 
     if (t == 0) {
         P.result[0] = win;
         P.result[1] = (int)(best >> 32);
-        P.result[2] = P.pose ? (int)P.valid[win] : 0;
-        P.result[3] = 0;
+        P.result[2] = P.pose ? (int)(P.valid[win] & 0xfu) : 0;
+        P.result[3] = n_deg;
         s_off = 0;
     }
     if (P.best) {
@@ -239,7 +248,6 @@ int run_ransac(SfmCtx* ctx, void* stream, const double* p1, const double* p2, in
     }
     SFM_LAUNCH(ctx, st, "k_ransac_fit", k_ransac_fit<<<ceil_div(iters, 64), 64, 0, st>>>(P));
     if (pose) {
-        SFM_CUDA_CHECK(ctx, cudaMemsetAsync(P.valid, 0, (size_t)iters * sizeof(uint32_t), st));
         SFM_LAUNCH(ctx, st, "k_ransac_valid", k_ransac_valid<<<iters, 128, 0, st>>>(P));
     }
     SFM_LAUNCH(ctx, st, "k_ransac_score", k_ransac_score<<<ceil_div(iters, 8), 256, 0, st>>>(P));

@@ -116,7 +116,11 @@ SFM_HD __forceinline__ void normalize8(const double* x, const double* y, double*
 }
 
 // SFM.py:189-236.
-SFM_HD void fundamental_8pt(const double* x1, const double* y1, const double* x2, const double* y2, double* F) {
+// `degenerate` (may be null) is set when the 8x9 design matrix is numerically rank-deficient (repeated or
+// co-motion-free correspondences): its null space then has more than one dimension and the vector LAPACK
+// returns for it -- hence the reference's F for this sample -- is decided by rounding noise.
+SFM_HD void fundamental_8pt(const double* x1, const double* y1, const double* x2, const double* y2, double* F,
+                            bool* degenerate = nullptr) {
     double a1[8], b1[8], a2[8], b2[8], s1, t1x, t1y, s2, t2x, t2y;
     normalize8(x1, y1, a1, b1, s1, t1x, t1y);
     normalize8(x2, y2, a2, b2, s2, t2x, t2y);
@@ -131,12 +135,14 @@ SFM_HD void fundamental_8pt(const double* x1, const double* y1, const double* x2
     // Householder QR of B; the last column of Q spans the null space of A (np.linalg.svd(A)[2][-1]
     // up to sign when A has rank 8).
     double tau[8];
+    double dmin = INFINITY, dmax = 0.0;                     // |diagonal of R|: its spread measures the rank
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         double nrm2 = 0.0;
 #pragma unroll
         for (int r = j; r < 9; ++r) nrm2 = fma(B[r][j], B[r][j], nrm2);
         const double nrm = sqrt(nrm2);
+        dmin = fmin(dmin, nrm); dmax = fmax(dmax, nrm);
         if (nrm == 0.0) { tau[j] = 0.0; continue; }
         const double alpha = B[j][j];
         const double beta = -copysign(nrm, alpha);
@@ -155,6 +161,7 @@ SFM_HD void fundamental_8pt(const double* x1, const double* y1, const double* x2
             for (int r = j + 1; r < 9; ++r) B[r][c] = fma(-w, B[r][j], B[r][c]);
         }
     }
+    if (degenerate) *degenerate = !(dmin > 1e-10 * dmax);
     double z[9] = {0, 0, 0, 0, 0, 0, 0, 0, 1.0};
 #pragma unroll
     for (int j = 7; j >= 0; --j) {

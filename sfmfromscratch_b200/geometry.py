@@ -79,7 +79,8 @@ def ransac_device(p1: torch.Tensor, p2: torch.Tensor, iterations: int, threshold
     """sfm_find_inliers / sfm_ransac_camera_motion on float64 CUDA tensors [n,2].
 
     Returns (inlier_idx [n] int32, result [4] int32, best [57] f64[, workspace]) as device tensors:
-    result = (winner or -1, inlier count, valid-candidate bits, 0); best = winner's F (9) followed,
+    result = (winner or -1, inlier count, valid-candidate bits, number of degenerate samples -- see
+    include/sfmb200.h: 0 means the outcome is the reference's to the index); best = winner's F (9) followed,
     in pose mode, by its four candidates (R row-major, T)."""
     if not (p1.is_cuda and p2.is_cuda) or p1.dtype != torch.float64 or p2.dtype != torch.float64 \
             or p1.dim() != 2 or p1.shape[1] != 2 or p1.shape != p2.shape:

@@ -65,6 +65,23 @@ def gather_descriptors(desc: torch.Tensor, counts: torch.Tensor, group=None):
     return out_d, out_c
 
 
+def gather_keypoints(x: torch.Tensor, y: torch.Tensor, group=None):
+    """All-gather the per-rank keypoint coordinates [b, cap] (int32) into [world*b, cap] on every
+    rank: the geometry stage of a pair needs the coordinates of both images (Runner.py:347)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return x, y
+    world = dist.get_world_size(group)
+    xy = torch.stack([x, y], dim=0).contiguous()                       # [2, b, cap]
+    out = torch.empty((world,) + tuple(xy.shape), dtype=xy.dtype, device=xy.device)
+    try:
+        dist.all_gather_into_tensor(out, xy, group=group)
+    except (RuntimeError, NotImplementedError):
+        dist.all_gather(list(out.unbind(0)), xy, group=group)
+    b = x.shape[0]
+    return (out[:, 0].reshape(world * b, -1), out[:, 1].reshape(world * b, -1))
+
+
 class GraphedExtractor:
     """sfm_extract_batch for a fixed batch shape captured once into a CUDA graph: the ~25 kernel
     launches of an extraction replay as one submission (what matters for a single image, where
@@ -189,6 +206,35 @@ class FeaturePipeline:
             self.params.cand_full = 1
             return self.run_host(host_images, pairs_global, host_out, chunk)
         return mine
+
+    def pair_inliers(self, x_all: torch.Tensor, y_all: torch.Tensor, match, pairs_mine: np.ndarray, iterations: int,
+                     threshold: float = 1.0, num_matches: int = 2500, threads: int = 8):
+        """The reference's per-pair tail (Runner.py:347-351) for this rank's pairs, device-resident:
+        matches -> coordinates (`sfm_matches_to_coords`) -> `find_inliers` (`sfm_find_inliers`).  Pairs are
+        independent, so the stage shards with the pairs and needs no collective beyond the keypoint
+        gather.  `match` is the tuple `self.match` returned for `pairs_mine`.  One host read of the match
+        counts sizes the 8-subset draws, which run on `threads` host threads while the kernels queue.
+        Returns a list, one entry per pair: None (fewer than 8 matches: the reference returns Nones), or
+        (p1 [n,2] f64, p2, inlier_idx [n] i32, result [4] i32) device tensors."""
+        from concurrent.futures import ThreadPoolExecutor
+        from . import geometry as GE
+        matches, _, mcount = match[0], match[1], match[2]
+        counts = np.minimum(mcount.cpu().numpy(), num_matches)
+        todo = [k for k in range(len(pairs_mine)) if counts[k] >= 8]
+        out: List[Optional[tuple]] = [None] * len(pairs_mine)
+        if not todo or iterations < 1:
+            return out
+        with ThreadPoolExecutor(max_workers=max(1, threads)) as ex:
+            samples = list(ex.map(lambda k: GE._samples_host(int(counts[k]), int(iterations), GE.RANSAC_SEED), todo))
+        for k, smp in zip(todo, samples):
+            i, j = int(pairs_mine[k][0]), int(pairs_mine[k][1])
+            p1, p2, _ = GE.matches_to_coords_device(matches[k], mcount[k:k + 1], x_all[i], y_all[i], x_all[j], y_all[j],
+                                                    num_matches)
+            n = int(counts[k])
+            idx, res, _ = GE.ransac_device(p1[:n], p2[:n], iterations, threshold,
+                                           samples=smp.to(p1.device, non_blocking=True))
+            out[k] = (p1[:n], p2[:n], idx, res)
+        return out
 
     def step(self, images: torch.Tensor, pairs_global: np.ndarray):
         """Extract the local images, all-gather, match this rank's share of `pairs_global`."""

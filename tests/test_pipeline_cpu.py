@@ -48,6 +48,10 @@ def _worker(rank, world, port, q):
         ok = d.shape == (world * b, nmax, 128) and c.tolist() == [1, 2, 3, 2, 3, 4]
         ok = ok and all(float(d[r * b + i, 0, 0]) == i + 10 * r and float(d[r * b + i, 0, 1]) == r
                         for r in range(world) for i in range(b))
+        x = torch.arange(b * 4, dtype=torch.int32).reshape(b, 4) + 100 * rank
+        gx, gy = P.gather_keypoints(x, x + 1000)
+        ok = ok and gx.shape == (world * b, 4) and all(int(gx[r * b + i, j]) == i * 4 + j + 100 * r and int(gy[r * b + i, j]) == i * 4 + j + 100 * r + 1000
+                                                       for r in range(world) for i in range(b) for j in range(4))
         pairs = P.consecutive_pairs(world * b)
         mine = P.deal_pairs(pairs, rank, world, block=2)
         q.put((rank, bool(ok), mine.tolist()))
