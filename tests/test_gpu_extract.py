@@ -95,6 +95,9 @@ def test_naive_sift_golden(golden_dir):
     (256, 256, 4, {'ksize': 9, 'gaussian_size': 5, 'sigma': 1.5, 'feature_width': 8, 'pyramid_level': 2}),
     (200, 300, 5, {'pyramid_level': 1}),
     (48, 64, 6, {'pyramid_level': 5}),
+    (150, 210, 7, {'ksize': 1, 'pyramid_level': 2}),              # 1x1 NMS window: every pixel at or above the median
+    (222, 318, 8, {'ksize': 5, 'gaussian_size': 3}),
+    (190, 254, 9, {'ksize': 11, 'gaussian_size': 9, 'num_interest_points': 900}),
 ])
 def test_scale_rot_inv_vs_oracle(h, w, seed, params):
     O, S, _ = _mods()
