@@ -207,6 +207,95 @@ class FeaturePipeline:
             return self.run_host(host_images, pairs_global, host_out, chunk)
         return mine
 
+    def stream_host(self, host_images: torch.Tensor, pairs_global: np.ndarray, host_out: dict, chunk: int = 8):
+        """`run_host` for a SEQUENCE of batches: nothing here waits on the host, so the host-to-device copy of
+        batch k+1 runs under the matching / read-back tail of batch k (a lone `run_host` leaves the PCIe link
+        idle for ~1 ms per step at both ends).  Device buffers are two persistent slots used alternately; a slot
+        is recycled only after the kernels and copies of the batch that used it two calls ago have finished
+        (events, no host sync).  Pass a different `host_out` to consecutive calls and read one only after
+        `drain()` (or after the event this returns has completed).  Returns (pairs of this rank, completion
+        event); candidate-overflow flags are checked in `drain()`."""
+        from .extractor import extract_batch_device
+        dev = torch.device('cuda', torch.cuda.current_device())
+        main = torch.cuda.current_stream()
+        if not hasattr(self, '_s_in'):
+            self._s_in, self._s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        B, H, W = host_images.shape
+        cap = host_out['x'].shape[1]
+        key = (B, H, W, cap, dev.index)
+        if getattr(self, '_slots_key', None) != key:
+            self.drain()
+            i32 = dict(dtype=torch.int32, device=dev)
+            self._slots = [{'imgs': torch.empty((B, H, W), dtype=torch.float32, device=dev),
+                            'x': torch.empty((B, cap), **i32), 'y': torch.empty((B, cap), **i32),
+                            'count': torch.empty((B,), **i32),
+                            'desc': torch.empty((B, cap, 128), dtype=torch.float32, device=dev),
+                            'hflags': torch.zeros((B,), dtype=torch.int32).pin_memory(),
+                            'imgs_free': None, 'out_free': None} for _ in range(2)]
+            self._slots_key, self._slot_i, self._pending = key, 0, []
+            main.synchronize()
+        slot = self._slots[self._slot_i]
+        self._slot_i ^= 1
+        imgs = slot['imgs']
+        full = {k: slot[k] for k in ('x', 'y', 'count', 'desc')}
+        if slot['imgs_free'] is not None:
+            self._s_in.wait_event(slot['imgs_free'])            # the extraction that last read this image slot is done
+        if slot['out_free'] is not None:
+            main.wait_event(slot['out_free'])                   # the read-back of this slot's previous results is done
+        bounds = [(c0, min(c0 + chunk, B)) for c0 in range(0, B, chunk)]
+        ready = []
+        with torch.cuda.stream(self._s_in):
+            for c0, c1 in bounds:
+                imgs[c0:c1].copy_(host_images[c0:c1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._s_in)
+                ready.append(ev)
+        hflags = slot['hflags']                                 # overflow flags land in pinned memory with the results:
+        for ci, ((c0, c1), ev) in enumerate(zip(bounds, ready)):    # reading them later needs no device-wide wait
+            main.wait_event(ev)
+            res = extract_batch_device(imgs[c0:c1], self.params, want_aux=False, check=False,
+                                       out={k: v[c0:c1] for k, v in full.items()})
+            hflags[ci:ci + 1].copy_(res['_flag'], non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            self._s_out.wait_event(done)
+            with torch.cuda.stream(self._s_out):
+                for k in ('x', 'y', 'desc', 'count'):
+                    host_out[k][c0:c1].copy_(full[k][c0:c1], non_blocking=True)
+        slot['imgs_free'] = torch.cuda.Event()
+        slot['imgs_free'].record(main)
+        desc_all, counts_all = self.exchange(full['desc'], full['count'])
+        pkey = (pairs_global.tobytes(), self.rank, self.world, self.pair_block, dev.index)
+        if getattr(self, '_pairs_key', None) != pkey:            # the pair list rarely changes: upload it once
+            mine = deal_pairs(pairs_global, self.rank, self.world, block=self.pair_block)
+            self._pairs_key, self._pairs_mine = pkey, mine
+            self._pairs_dev = torch.from_numpy(np.ascontiguousarray(mine)).to(dev) if len(mine) else None
+        mine = self._pairs_mine
+        if len(mine):
+            m = self.match(desc_all, counts_all, self._pairs_dev, cap=host_out['matches'].shape[1], pairs_host=mine)
+            host_out['matches'][:len(mine)].copy_(m[0], non_blocking=True)
+            host_out['conf'][:len(mine)].copy_(m[1], non_blocking=True)
+            host_out['mcount'][:len(mine)].copy_(m[2], non_blocking=True)
+        main.wait_stream(self._s_out)
+        slot['out_free'] = torch.cuda.Event()
+        slot['out_free'].record(main)
+        self._pending.append((slot['out_free'], hflags, len(bounds)))
+        while len(self._pending) > 1:                           # a slot's flags are overwritten two calls later: retire
+            ev, hf, nch = self._pending.pop(0)                  # the previous batch now (waits for that batch only)
+            ev.synchronize()
+            self._overflow = getattr(self, '_overflow', False) or bool(hf[:nch].any())
+        return mine, slot['out_free']
+
+    def drain(self) -> bool:
+        """Wait for every batch given to `stream_host`; True when no candidate buffer overflowed (otherwise set
+        `params.cand_full = 1` and resubmit the affected batches)."""
+        ok = not getattr(self, '_overflow', False)
+        for ev, hf, nch in getattr(self, '_pending', []):
+            ev.synchronize()
+            ok = ok and not bool(hf[:nch].any())
+        self._pending, self._overflow = [], False
+        return ok
+
     def pair_inliers(self, x_all: torch.Tensor, y_all: torch.Tensor, match, pairs_mine: np.ndarray, iterations: int,
                      threshold: float = 1.0, num_matches: int = 2500, threads: int = 8):
         """The reference's per-pair tail (Runner.py:347-351) for this rank's pairs, device-resident:

@@ -243,3 +243,66 @@ def test_run_host_pipeline_equals_plain_calls():
         if n:
             assert np.array_equal(out['matches'][k, :n].numpy().astype(np.int64), m)
             assert np.array_equal(out['conf'][k, :n].numpy(), c)
+
+
+def test_stream_host_equals_run_host():
+    """FeaturePipeline.stream_host (no host wait between batches, two device slots recycled by events)
+    delivers, for every batch of a sequence, exactly what run_host delivers for that batch alone."""
+    import torch
+    from sfmfromscratch_b200 import pipeline as PL
+    from sfmfromscratch_b200.synth import synth_image
+    B, H, W, cap = 6, 96, 128, 2500
+    pairs = PL.consecutive_pairs(B)
+
+    def outs():
+        return {'x': torch.zeros((B, cap), dtype=torch.int32).pin_memory(), 'y': torch.zeros((B, cap), dtype=torch.int32).pin_memory(),
+                'desc': torch.zeros((B, cap, 128), dtype=torch.float32).pin_memory(), 'count': torch.zeros((B,), dtype=torch.int32).pin_memory(),
+                'matches': torch.zeros((len(pairs), cap, 2), dtype=torch.int32).pin_memory(),
+                'conf': torch.zeros((len(pairs), cap), dtype=torch.float32).pin_memory(),
+                'mcount': torch.zeros((len(pairs),), dtype=torch.int32).pin_memory()}
+    batches = [torch.from_numpy(np.stack([synth_image(H, W, 100 * k + s) for s in range(B)])).pin_memory() for k in range(5)]
+    pipe = PL.FeaturePipeline({}, 0.8)
+    got = [outs() for _ in batches]
+    for hb, o in zip(batches, got):
+        pipe.stream_host(hb, pairs, o, chunk=4)
+    assert pipe.drain()
+    single = PL.FeaturePipeline({}, 0.8)
+    for hb, o in zip(batches, got):
+        ref = outs()
+        single.run_host(hb, pairs, ref, chunk=4)
+        assert np.array_equal(o['count'].numpy(), ref['count'].numpy()) and np.array_equal(o['mcount'].numpy(), ref['mcount'].numpy())
+        for b in range(B):
+            n = int(ref['count'][b])
+            for k in ('x', 'y', 'desc'):
+                assert np.array_equal(o[k][b, :n].numpy(), ref[k][b, :n].numpy())
+        for k in range(len(pairs)):
+            n = int(ref['mcount'][k])
+            assert np.array_equal(o['matches'][k, :n].numpy(), ref['matches'][k, :n].numpy())
+            assert np.array_equal(o['conf'][k, :n].numpy(), ref['conf'][k, :n].numpy())
+
+
+def test_stream_host_reports_candidate_overflow():
+    """A plateau image (all responses tie) overflows the density-sized candidate buffer: stream_host does not
+    wait on the host, so the flag travels to pinned memory with the results and drain() reports it."""
+    import torch
+    from sfmfromscratch_b200 import pipeline as PL
+    from sfmfromscratch_b200.synth import synth_image
+    B, H, W, cap = 4, 96, 128, 2500
+    pairs = PL.consecutive_pairs(B)
+    good = np.stack([synth_image(H, W, s) for s in range(B)])
+    bad = good.copy()
+    bad[2] = 0.0
+    out = {'x': torch.zeros((B, cap), dtype=torch.int32).pin_memory(), 'y': torch.zeros((B, cap), dtype=torch.int32).pin_memory(),
+           'desc': torch.zeros((B, cap, 128), dtype=torch.float32).pin_memory(), 'count': torch.zeros((B,), dtype=torch.int32).pin_memory(),
+           'matches': torch.zeros((len(pairs), cap, 2), dtype=torch.int32).pin_memory(),
+           'conf': torch.zeros((len(pairs), cap), dtype=torch.float32).pin_memory(),
+           'mcount': torch.zeros((len(pairs),), dtype=torch.int32).pin_memory()}
+    pipe = PL.FeaturePipeline({}, 0.8)
+    pipe.stream_host(torch.from_numpy(good).pin_memory(), pairs, out, chunk=2)
+    assert pipe.drain()
+    pipe.stream_host(torch.from_numpy(bad).pin_memory(), pairs, out, chunk=2)
+    pipe.stream_host(torch.from_numpy(good).pin_memory(), pairs, out, chunk=2)
+    assert not pipe.drain()                                     # the plateau batch is reported, even when retired early
+    pipe.params.cand_full = 1
+    pipe.stream_host(torch.from_numpy(bad).pin_memory(), pairs, out, chunk=2)
+    assert pipe.drain()
