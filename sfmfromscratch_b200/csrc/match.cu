@@ -109,160 +109,230 @@ __device__ __forceinline__ void top2_push(Top2& s, float d, int j) {
 
 // ------------------------------------------------------------------ re-check of tensor-core candidates
 
-// Warp per query row.  Entries of the row's candidate lists are visited in
-// increasing approximate key; each visit evaluates the 4 columns of the group
-// exactly (8 lanes per column, lane j owns numpy's accumulator r[j]).  The row
-// is certified when every unvisited or untracked column is provably farther
-// than the exact second-nearest found: approx_key + |a|^2 - E > d1^2, with E a
+// Eight lanes per query row, four rows per warp.  Entries of the row's
+// candidate lists are visited in increasing approximate key; each visit
+// evaluates the 4 columns of the group exactly.  The gather is bound by L1TEX
+// wavefronts (one per 128-byte line an instruction touches), so the team reads
+// every column as four full lines (lane k takes the k-th 16 bytes), forms the
+// squares (a - b)^2 where they land, and passes them through a padded
+// shared-memory staging row to the summation layout: lane (c, h) owns column c
+// of the group and numpy's accumulators r[4h .. 4h+3], adds its sixteen
+// float4 in order, and the tree ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) closes
+// with one shuffle.  The row is
+// certified when every unvisited or untracked column is provably farther than
+// the exact second-nearest found: approx_key + |a|^2 - E > d1^2, with E a
 // rigorous bound on |approx - exact| (fp16 rounding of both operands by
 // Cauchy-Schwarz on the residual norms, accumulation, index packing, and the
 // float32 rounding of the exact sum itself).  Uncertified rows go to the exact
-// scan.
-__global__ void __launch_bounds__(256) k_match_recheck(const __grid_constant__ MatchPlan P) {
+// scan.  NV = candidate entries per lane (ceil(n_lists * 4 / 8)).
+constexpr int RC_ROWS = 32;            // rows per CTA (256 threads)
+constexpr int RC_SQ_STRIDE = SFM_DESC_DIM + 8;   // staging row of squares: 544 bytes keeps the 4 columns on distinct banks
+
+template <int NV>
+__global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant__ MatchPlan P) {
+    extern __shared__ __align__(16) unsigned char rc_smem[];
+    float (*s_sq)[MT_GROUP][RC_SQ_STRIDE] = reinterpret_cast<float (*)[MT_GROUP][RC_SQ_STRIDE]>(rc_smem);
+    __shared__ int s_visited;
     const int p = P.p0 + blockIdx.y;
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int team = threadIdx.x >> 3, j = threadIdx.x & 7;
+    const int c = j & 3, h = j >> 2;
+    const unsigned tmask = 0xffu << (threadIdx.x & 24);
+    const int row = blockIdx.x * RC_ROWS + team;
     const int qa = P.pairs[2 * p], qb = P.pairs[2 * p + 1];
     const int n1 = P.set_cnt[qa], n2 = P.set_cnt[qb];
-    if (row >= n1 || n2 < 2) return;                       // n2 < 2: the pair emits nothing
-    const float* A = P.set_ptr[qa] + (size_t)row * SFM_DESC_DIM;
-    const float* B = P.set_ptr[qb];
-    const size_t arow = (size_t)qa * P.nmax_pad + row;
-    const double na = (double)P.nb[arow];
-    const double hat_a = (double)P.hatn[arow], res_a = (double)P.resn[arow];
-    const double mh = (double)P.setmax[4 * qb + 0], mr = (double)P.setmax[4 * qb + 1], mnb = (double)P.setmax[4 * qb + 2];
-    const double e_fp16 = 2.0 * (hat_a * mr + res_a * mh + res_a * mr);
-    const double e_acc = 2.0 * hat_a * mh * (1.0 / 262144.0);                   // 2^-18
-    const double e_ref = (na + mnb + 2.0 * sqrt(na * mnb)) * (1.0 / 524288.0);  // 2^-19 * dmax^2
-    const double e_nrm = (na + mnb) * (1.0 / 131072.0);                         // 2^-17
-    const double e_base = 1.1 * (e_fp16 + e_acc + e_ref + e_nrm) + 1e-12;
-    const double q_rel = 1.1 / 8192.0 * 2.0;                                    // packing drops 10 mantissa bits
-
-    const int E = P.n_lists * MT_TOPK;
-    const uint32_t* lists = P.cands + ((size_t)p * P.nmax_pad + row) * (size_t)E;
-    float val[4];
-    uint32_t code[4];
-    float Lmin = INFINITY;
+    if (threadIdx.x == 0) s_visited = 0;
+    __syncthreads();
+    int visited = 0;
+    if (row < n1 && n2 >= 2) {                             // n2 < 2: the pair emits nothing
+        const float* B = P.set_ptr[qb];
+        float4 a4[4];                                      // elements 32 i + 4 j .. + 3 of the query row
+        {
+            const float4* A4 = reinterpret_cast<const float4*>(P.set_ptr[qa] + (size_t)row * SFM_DESC_DIM);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int e = lane + 32 * i;
-        val[i] = INFINITY; code[i] = 0;
-        if (e < E) {
-            const uint32_t pk = lists[e];
-            const float v = __uint_as_float(pk & ~MT_IDX_MASK);
-            if (v < MT_INVALID) {
-                val[i] = v;
-                code[i] = ((uint32_t)(e / MT_TOPK) << MT_IDX_BITS) | (pk & MT_IDX_MASK);
-                if ((e % MT_TOPK) == MT_TOPK - 1) Lmin = fminf(Lmin, v);
+            for (int i = 0; i < 4; ++i) a4[i] = A4[j + 8 * i];
+        }
+        const int E = P.n_lists * MT_TOPK;
+        const uint32_t* lists = P.cands + ((size_t)p * P.nmax_pad + row) * (size_t)E;
+        float val[NV];
+        uint32_t code[NV];
+        float Lmin = INFINITY;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int e = j + 8 * i;
+            val[i] = INFINITY; code[i] = 0;
+            if (e < E) {
+                const uint32_t pk = lists[e];
+                const float v = __uint_as_float(pk & ~MT_IDX_MASK);
+                if (v < MT_INVALID) {
+                    val[i] = v;
+                    code[i] = ((uint32_t)(e / MT_TOPK) << MT_IDX_BITS) | (pk & MT_IDX_MASK);
+                    if ((e % MT_TOPK) == MT_TOPK - 1) Lmin = fminf(Lmin, v);
+                }
             }
         }
-    }
-    for (int o = 16; o > 0; o >>= 1) Lmin = fminf(Lmin, __shfl_xor_sync(0xffffffffu, Lmin, o));
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) Lmin = fminf(Lmin, __shfl_xor_sync(tmask, Lmin, o, 8));
 
-    float a[16];
-    const int j = lane & 7, team = lane >> 3;
-#pragma unroll
-    for (int m = 0; m < 16; ++m) a[m] = A[8 * m + j];
+        const size_t arow = (size_t)qa * P.nmax_pad + row;
+        const double na = (double)P.nb[arow];
+        const double hat_a = (double)P.hatn[arow], res_a = (double)P.resn[arow];
+        const double mh = (double)P.setmax[4 * qb + 0], mr = (double)P.setmax[4 * qb + 1], mnb = (double)P.setmax[4 * qb + 2];
+        const double e_fp16 = 2.0 * (hat_a * mr + res_a * mh + res_a * mr);
+        const double e_acc = 2.0 * hat_a * mh * (1.0 / 262144.0);                   // 2^-18
+        const double e_ref = (na + mnb + 2.0 * sqrt(na * mnb)) * (1.0 / 524288.0);  // 2^-19 * dmax^2
+        const double e_nrm = (na + mnb) * (1.0 / 131072.0);                         // 2^-17
+        const double e_base = 1.1 * (e_fp16 + e_acc + e_ref + e_nrm) + 1e-12;
+        const double q_rel = 1.1 / 8192.0 * 2.0;                                    // packing drops 10 mantissa bits
 
-    Top2 best = {INFINITY, -1, INFINITY};
-    int visited = 0;
+        Top2 best = {INFINITY, -1, INFINITY};
 
-    // smallest unvisited entry across the warp (marks it visited); false when none is left
-    auto pop_min = [&](float& wv, uint32_t& wc) -> bool {
-        float bv = INFINITY; uint32_t bc = 0; int bi = -1;
+        // smallest unvisited entry of the team: its value (INFINITY when none is left), owner lane and slot
+        auto find_min = [&](float& wv, int& wl, int& bi, uint32_t& bc) {
+            float bv = INFINITY; bc = 0; bi = -1;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) if (val[i] < bv) { bv = val[i]; bc = code[i]; bi = i; }
-        wv = bv;
-        int wl = (bi >= 0) ? lane : 64;
-        for (int o = 16; o > 0; o >>= 1) {
-            const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
-            const int ol = __shfl_xor_sync(0xffffffffu, wl, o);
-            if (ov < wv || (ov == wv && ol < wl)) { wv = ov; wl = ol; }
-        }
-        if (wl >= 32) return false;
-        wc = __shfl_sync(0xffffffffu, bc, wl);
-        if (lane == wl) {
+            for (int i = 0; i < NV; ++i) if (val[i] < bv) { bv = val[i]; bc = code[i]; bi = i; }
+            wv = bv;
+            wl = (bi >= 0) ? j : 64;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) if (i == bi) val[i] = INFINITY;
-        }
-        return true;
-    };
-    auto group_col = [&](uint32_t wc) -> int {
-        const int list = (int)(wc >> MT_IDX_BITS);
-        const int split = list >> 1, half = list & 1;
-        const int tile = split * P.tiles_per_split + (int)((wc & MT_IDX_MASK) >> 4);
-        return tile * MT_COLS + half * 64 + (int)(wc & 15u) * MT_GROUP + team;
-    };
-    // numpy-order partial sum of this lane's accumulator r[j] against column `colc`
-    auto lane_acc = [&](int colc) -> float {
-        const float* bq = B + (size_t)colc * SFM_DESC_DIM + j;
-        const float t0 = __fsub_rn(a[0], bq[0]);
-        float r = __fmul_rn(t0, t0);
+            for (int o = 4; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(tmask, wv, o, 8);
+                const int ol = __shfl_xor_sync(tmask, wl, o, 8);
+                if (ov < wv || (ov == wv && ol < wl)) { wv = ov; wl = ol; }
+            }
+        };
+        auto consume = [&](int wl, int bi, uint32_t bc) -> uint32_t {
+            const uint32_t wc = __shfl_sync(tmask, bc, wl & 7, 8);
+            if (j == wl) {
 #pragma unroll
-        for (int m = 1; m < 16; ++m) {
-            const float tt = __fsub_rn(a[m], bq[8 * m]);
-            r = __fadd_rn(r, __fmul_rn(tt, tt));
-        }
-        return r;
-    };
-    auto tree = [&](float r) -> float {
-        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));   // (r0+r1) ...
-        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 2));   // (r0+r1)+(r2+r3)
-        r = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 4));   // full tree
-        return r;
-    };
-    auto push_group = [&](float d2, int col) {
+                for (int i = 0; i < NV; ++i) if (i == bi) val[i] = INFINITY;
+            }
+            return wc;
+        };
+        auto group_col = [&](uint32_t wc) -> int {
+            const int list = (int)(wc >> MT_IDX_BITS);
+            const int split = list >> 1, half = list & 1;
+            const int tile = split * P.tiles_per_split + (int)((wc & MT_IDX_MASK) >> 4);
+            return tile * MT_COLS + half * 64 + (int)(wc & 15u) * MT_GROUP;
+        };
+        // the group's 4 columns as full lines: v[4 cc + i] = elements 32 i + 4 j .. + 3 of column col0 + cc
+        auto group_load = [&](int col0, float4 (&v)[16]) {
 #pragma unroll
-        for (int tm = 0; tm < 4; ++tm) {
-            const float dd = __shfl_sync(0xffffffffu, d2, tm * 8);
-            const int cc = col - team + tm;
-            if (cc < n2) top2_push(best, dd, cc);
-        }
-        ++visited;
-    };
+            for (int cc = 0; cc < MT_GROUP; ++cc) {
+                const float4* bp = reinterpret_cast<const float4*>(B + (size_t)min(col0 + cc, n2 - 1) * SFM_DESC_DIM) + j;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[4 * cc + i] = bp[8 * i];
+            }
+        };
+        // squares (a - b)^2 of a loaded group into the team's staging rows, in the columns' own element order
+        auto stage_squares = [&](const float4 (&v)[16]) {
+#pragma unroll
+            for (int cc = 0; cc < MT_GROUP; ++cc)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 b = v[4 * cc + i], a = a4[i];
+                    float4 q;
+                    float t;
+                    t = __fsub_rn(a.x, b.x); q.x = __fmul_rn(t, t);
+                    t = __fsub_rn(a.y, b.y); q.y = __fmul_rn(t, t);
+                    t = __fsub_rn(a.z, b.z); q.z = __fmul_rn(t, t);
+                    t = __fsub_rn(a.w, b.w); q.w = __fmul_rn(t, t);
+                    *reinterpret_cast<float4*>(&s_sq[team][cc][32 * i + 4 * j]) = q;
+                }
+            __syncwarp(tmask);
+        };
+        // numpy's summation of the staged squares of column c; every lane of the team gets its column's squared distance
+        auto sum_staged = [&]() -> float {
+            const float4* sp = reinterpret_cast<const float4*>(&s_sq[team][c][4 * h]);
+            float4 x = sp[0];
+#pragma unroll
+            for (int m = 1; m < 16; ++m) {
+                const float4 y = sp[2 * m];
+                x.x = __fadd_rn(x.x, y.x); x.y = __fadd_rn(x.y, y.y);
+                x.z = __fadd_rn(x.z, y.z); x.w = __fadd_rn(x.w, y.w);
+            }
+            __syncwarp(tmask);                                                  // staging rows are reused by the next group
+            const float s4 = __fadd_rn(__fadd_rn(x.x, x.y), __fadd_rn(x.z, x.w));   // (r0+r1)+(r2+r3) or (r4+r5)+(r6+r7)
+            return __fadd_rn(s4, __shfl_xor_sync(tmask, s4, 4, 8));
+        };
+        auto push_group = [&](float d2, int col0) {
+#pragma unroll
+            for (int tm = 0; tm < MT_GROUP; ++tm) {
+                const float dd = __shfl_sync(tmask, d2, tm, 8);
+                if (col0 + tm < n2) top2_push(best, dd, col0 + tm);
+            }
+            ++visited;
+        };
 
-    // The two best entries are evaluated together (their loads overlap): the second one is needed
-    // in practice anyway, because four columns rarely certify a row.
-    float wv1, wv2; uint32_t wc1 = 0, wc2 = 0;
-    const bool have1 = pop_min(wv1, wc1);
-    const bool have2 = have1 && pop_min(wv2, wc2);
-    if (have2) {
-        const int col1 = group_col(wc1), col2 = group_col(wc2);
-        const float r1 = lane_acc(col1 < n2 ? col1 : n2 - 1);
-        const float r2 = lane_acc(col2 < n2 ? col2 : n2 - 1);
-        push_group(tree(r1), col1);
-        push_group(tree(r2), col2);
-    } else if (have1) {
-        const int col1 = group_col(wc1);
-        push_group(tree(lane_acc(col1 < n2 ? col1 : n2 - 1)), col1);
-    }
-    for (;;) {
-        float wv; uint32_t wc;
-        // peek: the stop test needs the smallest remaining value before it is consumed
-        float pv = INFINITY;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) pv = fminf(pv, val[i]);
-        for (int o = 16; o > 0; o >>= 1) pv = fminf(pv, __shfl_xor_sync(0xffffffffu, pv, o));
-        if (pv == INFINITY) break;                            // nothing left
-        const double bound = (double)pv + na - (e_base + q_rel * fabs((double)pv));
-        if (bound > (double)best.d1) break;                   // the rest cannot matter
-        if (!pop_min(wv, wc)) break;
-        const int col = group_col(wc);
-        push_group(tree(lane_acc(col < n2 ? col : n2 - 1)), col);
-    }
-    const bool certified =
-        (Lmin == INFINITY) ||
-        ((double)Lmin + na - (e_base + q_rel * fabs((double)Lmin)) > (double)best.d1);
-    if (lane == 0) {
-        if (P.stats) atomicAdd(&P.stats[2 * p + 1], visited);
-        if (certified && n2 >= 2) {
+        // The two best entries are evaluated together (their loads overlap): the second one is needed
+        // in practice anyway, because four columns rarely certify a row.
+        float wv; int wl, bi; uint32_t bc;
+        find_min(wv, wl, bi, bc);
+        if (wl < 8) {
+            const int col1 = group_col(consume(wl, bi, bc));
+            find_min(wv, wl, bi, bc);
+            if (wl < 8) {
+                const int col2 = group_col(consume(wl, bi, bc));
+                // the second group's loads are issued once the first one's registers are free and fly
+                // under its summation
+                float4 v[16];
+                group_load(col1, v);
+                stage_squares(v);
+                group_load(col2, v);
+                push_group(sum_staged(), col1);
+                stage_squares(v);
+                push_group(sum_staged(), col2);
+            } else {
+                float4 v[16];
+                group_load(col1, v);
+                stage_squares(v);
+                push_group(sum_staged(), col1);
+            }
+            for (;;) {
+                find_min(wv, wl, bi, bc);
+                if (wl >= 8) break;                               // nothing left
+                const double bound = (double)wv + na - (e_base + q_rel * fabs((double)wv));
+                if (bound > (double)best.d1) break;               // the rest cannot matter
+                const int col = group_col(consume(wl, bi, bc));
+                float4 v[16];
+                group_load(col, v);
+                stage_squares(v);
+                push_group(sum_staged(), col);
+            }
+        }
+        const bool certified =
+            (Lmin == INFINITY) ||
+            ((double)Lmin + na - (e_base + q_rel * fabs((double)Lmin)) > (double)best.d1);
+        if (j == 0) {
             const size_t o = (size_t)p * P.nmax + row;
-            P.res_idx[o] = best.i0; P.res_d0[o] = best.d0; P.res_d1[o] = best.d1;
-        } else {
-            const int pos = atomicAdd(&P.flag_cnt[p], 1);
-            P.flag_rows[(size_t)p * P.nmax + pos] = row;
+            if (certified) {
+                P.res_idx[o] = best.i0; P.res_d0[o] = best.d0; P.res_d1[o] = best.d1;
+            } else {
+                const int pos = atomicAdd(&P.flag_cnt[p], 1);
+                P.flag_rows[(size_t)p * P.nmax + pos] = row;
+            }
+            if (P.stats) atomicAdd(&s_visited, visited);
         }
     }
+    __syncthreads();
+    if (threadIdx.x == 0 && P.stats && s_visited) atomicAdd(&P.stats[2 * p + 1], s_visited);
+}
+
+static int launch_match_recheck(SfmCtx* ctx, cudaStream_t s, const MatchPlan& P) {
+    const dim3 grid(ceil_div(P.nmax, RC_ROWS), P.pn);
+    const int nv = ceil_div(P.n_lists * MT_TOPK, 8);
+    constexpr int smem = RC_ROWS * MT_GROUP * RC_SQ_STRIDE * (int)sizeof(float);
+#define RC_GO(NV)                                                                                          \
+    do {                                                                                                   \
+        SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_recheck<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+        SFM_LAUNCH(ctx, s, "k_match_recheck", k_match_recheck<NV><<<grid, 256, smem, s>>>(P));             \
+    } while (0)
+    if (nv <= 1) RC_GO(1);
+    else if (nv <= 2) RC_GO(2);
+    else if (nv <= 4) RC_GO(4);
+    else if (nv <= 8) RC_GO(8);
+    else RC_GO(16);
+#undef RC_GO
+    return SFM_OK;
 }
 
 // ------------------------------------------------------------------ exact tile scan
@@ -555,7 +625,8 @@ static int run_match_chunk(SfmCtx* ctx, cudaStream_t s, MatchPlan P, int p0, int
     if (P.mode == SFM_MATCH_AUTO) {
         int rc = launch_match_tc(ctx, s, P);
         if (rc) return rc;
-        SFM_LAUNCH(ctx, s, "k_match_recheck", k_match_recheck<<<dim3(ceil_div(P.nmax, 8), pn), 256, 0, s>>>(P));
+        rc = launch_match_recheck(ctx, s, P);
+        if (rc) return rc;
     } else {
         SFM_LAUNCH(ctx, s, "k_flag_all", k_flag_all<<<rowgrid, 256, 0, s>>>(P));
     }
