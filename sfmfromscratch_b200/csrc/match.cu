@@ -5,8 +5,10 @@
 //   k_match_tc       (match_tc.cu) tcgen05 fp16 GEMM tiles, fused top-4 groups
 //   k_match_recheck  exact float32 distances (numpy summation order) of the
 //                    candidate groups + error-bound certificate
-//   k_match_exact    exact tile scan of rows the certificate rejected
-//                    (all rows in SFM_MATCH_EXACT mode), k_match_merge
+//   k_match_rescan   rows the certificate rejected: float32 dot-product scan,
+//                    exact arithmetic for the columns within the bound
+//   k_match_exact    exact tile scan of every row (SFM_MATCH_EXACT mode)
+//   k_match_merge    partial results of either scan
 //   k_match_emit     d1 > 0, d0/d1 <= thr            (:46-51)
 //   k_match_sort     order by confidence             (:56-58)
 //
@@ -17,6 +19,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "match.cuh"
@@ -267,10 +270,29 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
         // in practice anyway, because four columns rarely certify a row.
         float wv; int wl, bi; uint32_t bc;
         find_min(wv, wl, bi, bc);
+        bool done = false;                                         // result already written (pruned row)
         if (wl < 8) {
+            const float k0 = wv;
             const int col1 = group_col(consume(wl, bi, bc));
             find_min(wv, wl, bi, bc);
-            if (wl < 8) {
+            // Ratio prune.  k0 <= k1 are the two smallest group keys, so the nearest exact distance is at
+            // least L0 = k0 + |a|^2 - E and the second-nearest (two distinct columns exist that close) at
+            // most U1 = k1 + |a|^2 + E.  When sqrt(L0 / U1) exceeds the threshold with room for the two
+            // float32 roundings of sqrt and divide, the reference's ratio test rejects the row whatever
+            // the exact values are: nothing is gathered (d1 = 0 makes k_match_emit skip the row).
+            bool pruned = false;
+            if (wl < 8 && P.thr >= 0.0f && !P.no_prune) {
+                const double em = e_base + q_rel * fmax(fabs((double)k0), fabs((double)wv));
+                const double L0 = (double)k0 + na - em, U1 = (double)wv + na + em;
+                pruned = L0 > 0.0 && L0 * (1.0 - 4e-6) > (double)P.thr * (double)P.thr * U1;
+            }
+            if (pruned) {
+                done = true;
+                if (j == 0) {
+                    const size_t o = (size_t)p * P.nmax + row;
+                    P.res_idx[o] = -1; P.res_d0[o] = 0.f; P.res_d1[o] = 0.f;
+                }
+            } else if (wl < 8) {
                 const int col2 = group_col(consume(wl, bi, bc));
                 // the second group's loads are issued once the first one's registers are free and fly
                 // under its summation
@@ -287,7 +309,7 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
                 stage_squares(v);
                 push_group(sum_staged(), col1);
             }
-            for (;;) {
+            while (!done) {
                 find_min(wv, wl, bi, bc);
                 if (wl >= 8) break;                               // nothing left
                 const double bound = (double)wv + na - (e_base + q_rel * fabs((double)wv));
@@ -302,16 +324,17 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
         const bool certified =
             (Lmin == INFINITY) ||
             ((double)Lmin + na - (e_base + q_rel * fabs((double)Lmin)) > (double)best.d1);
-        if (j == 0) {
+        if (j == 0 && !done) {
             const size_t o = (size_t)p * P.nmax + row;
             if (certified) {
                 P.res_idx[o] = best.i0; P.res_d0[o] = best.d0; P.res_d1[o] = best.d1;
             } else {
                 const int pos = atomicAdd(&P.flag_cnt[p], 1);
                 P.flag_rows[(size_t)p * P.nmax + pos] = row;
+                P.res_d1[o] = best.d1;                            // upper bound of the true second-nearest: the rescan's filter
             }
-            if (P.stats) atomicAdd(&s_visited, visited);
         }
+        if (j == 0 && P.stats) atomicAdd(&s_visited, visited);
     }
     __syncthreads();
     if (threadIdx.x == 0 && P.stats && s_visited) atomicAdd(&P.stats[2 * p + 1], s_visited);
@@ -458,6 +481,155 @@ __global__ void __launch_bounds__(256, 1) k_match_exact(const __grid_constant__ 
     }
 }
 
+// Filtered rescan of the rows the certificate rejected (tensor-core mode).  The re-check leaves an
+// exact upper bound d1 of each such row's second-nearest squared distance, so only columns that can
+// be at most that far need the reference's arithmetic.  The scan itself is a plain float32 FMA dot
+// product: approx = |a|^2 + |b|^2 - 2 a.b differs from the exact value by at most E' (dot-product
+// rounding by Cauchy-Schwarz, the norms, the float32 rounding of the exact sum), and a column is
+// evaluated exactly iff approx <= d1 + E'.
+// Work item = (pair, 8 flagged rows, 1024-column chunk), as in k_match_exact.  A warp takes one column
+// at a time as ONE coalesced 512-byte read (lane k holds elements 4k..4k+3 -- a thread-per-column
+// walk costs 32 L1TEX wavefronts per load instruction and was 8x slower), multiplies it with the
+// eight query rows it keeps in registers, and folds the 8 x 32 partial sums with a 9-shuffle
+// transpose-reduction that leaves row r's dot product in the lanes whose bits 4..2 spell r.  Each
+// lane keeps the rows in the order i -> row i ^ (its bits 4..2), which makes "the half I send" the
+// same registers in every lane (no selects).
+constexpr int RS_UNROLL = 4;
+
+__global__ void __launch_bounds__(256, 2) k_match_rescan(const __grid_constant__ MatchPlan P) {
+    __shared__ Top2 s_red[8][MX_ROWS];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int myrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+    const int32_t* wo = P.work_off + P.woff;
+    const int total = wo[P.pn];
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+        int lo = 0, hi = P.pn - 1;                             // last q with wo[q] <= w
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (wo[mid] <= w) lo = mid; else hi = mid - 1;
+        }
+        const int p = P.p0 + lo;
+        const int local = w - wo[lo];
+        const int rg = local / P.n_xchunks, ch = local - rg * P.n_xchunks;
+        const int qa = P.pairs[2 * p], qb = P.pairs[2 * p + 1];
+        const int n2 = P.set_cnt[qb];
+        const int nflag = P.flag_cnt[p];
+        const int col0 = ch * MX_COLS;
+        const int col1 = min(col0 + MX_COLS, n2);
+        // the eight query rows (lane k: elements 4k..4k+3 of each; a[i] is row i ^ myrow), this lane's row
+        // norm and threshold
+        float4 a[MX_ROWS];
+#pragma unroll
+        for (int r = 0; r < MX_ROWS; ++r) {
+            const int slot = rg * MX_ROWS + (r ^ myrow);
+            a[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (slot < nflag) {
+                const int row = P.flag_rows[(size_t)p * P.nmax + slot];
+                a[r] = reinterpret_cast<const float4*>(P.set_ptr[qa] + (size_t)row * SFM_DESC_DIM)[lane];
+            }
+        }
+        float my_na = 0.f, my_T = -INFINITY;                   // empty slot: nothing passes the filter
+        {
+            const int slot = rg * MX_ROWS + myrow;
+            if (slot < nflag) {
+                const int row = P.flag_rows[(size_t)p * P.nmax + slot];
+                my_na = P.nb[(size_t)qa * P.nmax_pad + row];
+                const double mnb = (double)P.setmax[4 * qb + 2];
+                const double dn = (double)my_na, ab = sqrt(dn * mnb);
+                const double e = 1.1 * (ab * (1.0 / 65536.0) + (dn + mnb) * (1.0 / 262144.0) +
+                                        (dn + mnb + 2.0 * ab) * (1.0 / 524288.0)) + 1e-12;
+                // rounded up: the comparison below is in float32
+                my_T = __double2float_ru((double)P.res_d1[(size_t)p * P.nmax + row] + e);
+            }
+        }
+        __syncthreads();                                       // previous item's s_red has been read
+        if (lane < MX_ROWS) s_red[warp][lane] = {INFINITY, -1, INFINITY};   // this warp's running top-2 per row (lane 0 updates)
+        __syncwarp();
+        const float* B = P.set_ptr[qb];
+        const float* nbq = P.nb + (size_t)qb * P.nmax_pad;
+
+        float4 nxt[RS_UNROLL];
+        float nxt_nb[RS_UNROLL];
+        auto fetch = [&](int jbase) {
+#pragma unroll
+            for (int u = 0; u < RS_UNROLL; ++u) {
+                const int jc = min(jbase + 8 * u, n2 - 1);
+                nxt[u] = reinterpret_cast<const float4*>(B + (size_t)jc * SFM_DESC_DIM)[lane];
+                nxt_nb[u] = nbq[jc];
+            }
+        };
+        fetch(col0 + warp);
+        for (int jb = col0 + warp; jb < col1; jb += 8 * RS_UNROLL) {
+            float4 cur[RS_UNROLL];
+            float cur_nb[RS_UNROLL];
+#pragma unroll
+            for (int u = 0; u < RS_UNROLL; ++u) { cur[u] = nxt[u]; cur_nb[u] = nxt_nb[u]; }
+            if (jb + 8 * RS_UNROLL < col1) fetch(jb + 8 * RS_UNROLL);
+#pragma unroll
+            for (int u = 0; u < RS_UNROLL; ++u) {
+                const int jc = jb + 8 * u;
+                if (jc >= col1) break;                         // warp-uniform
+                const float4 b = cur[u];
+                float d[MX_ROWS];
+#pragma unroll
+                for (int r = 0; r < MX_ROWS; ++r)
+                    d[r] = fmaf(a[r].w, b.w, fmaf(a[r].z, b.z, fmaf(a[r].y, b.y, a[r].x * b.x)));
+                // transpose-reduce: 8 rows x 32 lanes -> row (bits 4..2 of the lane), summed over all lanes
+                float e4[4], e2[2], e1;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) e4[r] = d[r] + __shfl_xor_sync(0xffffffffu, d[r + 4], 16);
+#pragma unroll
+                for (int r = 0; r < 2; ++r) e2[r] = e4[r] + __shfl_xor_sync(0xffffffffu, e4[r + 2], 8);
+                e1 = e2[0] + __shfl_xor_sync(0xffffffffu, e2[1], 4);
+                e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
+                e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
+                const float approx = fmaf(-2.0f, e1, my_na + cur_nb[u]);
+                unsigned hits = __ballot_sync(0xffffffffu, approx <= my_T) & 0x11111111u;
+                while (hits) {                                 // rare: the reference's arithmetic for (row r, column jc)
+                    const int src = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const int r = ((src >> 4) & 1) * 4 + ((src >> 3) & 1) * 2 + ((src >> 2) & 1);
+                    float4 av = a[0];                      // a[r ^ myrow] is row r
+#pragma unroll
+                    for (int rr = 1; rr < MX_ROWS; ++rr) if (rr == (r ^ myrow)) av = a[rr];
+                    // element 4k+q belongs to numpy's accumulator 4(k&1)+q at step k>>1: the running sums
+                    // walk down the lanes two at a time
+                    float tt;
+                    float4 run;
+                    tt = __fsub_rn(av.x, b.x); run.x = __fmul_rn(tt, tt);
+                    tt = __fsub_rn(av.y, b.y); run.y = __fmul_rn(tt, tt);
+                    tt = __fsub_rn(av.z, b.z); run.z = __fmul_rn(tt, tt);
+                    tt = __fsub_rn(av.w, b.w); run.w = __fmul_rn(tt, tt);
+                    const float4 sq = run;
+#pragma unroll 1
+                    for (int m = 1; m < 16; ++m) {
+                        const float px = __shfl_up_sync(0xffffffffu, run.x, 2);
+                        const float py = __shfl_up_sync(0xffffffffu, run.y, 2);
+                        const float pz = __shfl_up_sync(0xffffffffu, run.z, 2);
+                        const float pw = __shfl_up_sync(0xffffffffu, run.w, 2);
+                        if ((lane >> 1) == m) {
+                            run.x = __fadd_rn(px, sq.x); run.y = __fadd_rn(py, sq.y);
+                            run.z = __fadd_rn(pz, sq.z); run.w = __fadd_rn(pw, sq.w);
+                        }
+                    }
+                    const float s4 = __fadd_rn(__fadd_rn(run.x, run.y), __fadd_rn(run.z, run.w));  // lane 30: (r0+r1)+(r2+r3), lane 31: (r4+r5)+(r6+r7)
+                    const float d2 = __fadd_rn(__shfl_sync(0xffffffffu, s4, 30), __shfl_sync(0xffffffffu, s4, 31));
+                    if (lane == 0) top2_push(s_red[warp][r], d2, jc);
+                }
+            }
+        }
+        __syncthreads();
+        if (t < MX_ROWS) {
+            Top2 v = s_red[0][t];
+            for (int q = 1; q < 8; ++q) v = top2_merge(v, s_red[q][t]);
+            const int slot = rg * MX_ROWS + t;
+            if (slot < nflag)
+                P.part[((size_t)p * P.nmax + slot) * P.n_xchunks + ch] =
+                    make_float4(v.d0, __int_as_float(v.i0), v.d1, 0.f);
+        }
+    }
+}
+
 __global__ void k_match_merge(const __grid_constant__ MatchPlan P) {
     const int p = P.p0 + blockIdx.y;
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -495,19 +667,59 @@ __global__ void k_match_emit(const __grid_constant__ MatchPlan P) {
     }
 }
 
-// Rank sort by (confidence, query row): NNRatioFeatureMatcher.py:56-58 with the
-// tie order made canonical.
-__global__ void __launch_bounds__(256) k_match_sort(const __grid_constant__ MatchPlan P, int32_t* __restrict__ match_out,
-                                                    float* __restrict__ conf_out, int32_t* __restrict__ count_out,
-                                                    int32_t* __restrict__ stats_out) {
-    __shared__ unsigned long long s_k[256];
-    const int p = P.p0 + blockIdx.y;
+// Order by (confidence, query row): NNRatioFeatureMatcher.py:56-58 with the tie order made
+// canonical.  One CTA per pair sorts the pair's 64-bit keys (confidence bits << 32 | row) in shared
+// memory with a bitonic network; the matched index is looked up again through the row.  Pairs with
+// more matches than fit (SORT_SMEM_MAX) are left to the rank sort below.
+constexpr int SORT_SMEM_MAX = 8192;
+
+__global__ void __launch_bounds__(1024) k_match_sort(const __grid_constant__ MatchPlan P, int n2pow_max,
+                                                     int32_t* __restrict__ match_out, float* __restrict__ conf_out,
+                                                     int32_t* __restrict__ count_out, int32_t* __restrict__ stats_out) {
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    unsigned long long* s_k = reinterpret_cast<unsigned long long*>(sort_smem);
+    const int p = P.p0 + blockIdx.x;
     const int n = P.mcount[p];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
+    if (threadIdx.x == 0) {
         count_out[p] = n < P.cap ? n : P.cap;
         if (stats_out) { stats_out[2 * p] = P.flag_cnt[p]; stats_out[2 * p + 1] = P.stats[2 * p + 1]; }
     }
-    if ((int)blockIdx.x * 256 >= n) return;
+    if (n == 0 || n > n2pow_max) return;
+    int N2 = 32;
+    while (N2 < n) N2 <<= 1;
+    const unsigned long long* keys = P.mkeys + (size_t)p * P.nmax;
+    for (int i = threadIdx.x; i < N2; i += blockDim.x) s_k[i] = (i < n) ? keys[i] : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= N2; k <<= 1) {
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int i = threadIdx.x; i < (N2 >> 1); i += blockDim.x) {
+                const int lo = ((i & ~(jj - 1)) << 1) | (i & (jj - 1));
+                const int hi = lo | jj;
+                const unsigned long long x = s_k[lo], y = s_k[hi];
+                const bool up = (lo & k) == 0;
+                if ((x > y) == up) { s_k[lo] = y; s_k[hi] = x; }
+            }
+            __syncthreads();
+        }
+    }
+    const int lim = n < P.cap ? n : P.cap;
+    for (int r = threadIdx.x; r < lim; r += blockDim.x) {
+        const unsigned long long key = s_k[r];
+        const uint32_t row = (uint32_t)key;
+        const size_t o = (size_t)p * P.cap + r;
+        match_out[2 * o] = (int32_t)row;
+        match_out[2 * o + 1] = P.res_idx[(size_t)p * P.nmax + row];
+        conf_out[o] = __uint_as_float((uint32_t)(key >> 32));
+    }
+}
+
+// Rank sort for the pairs the shared-memory sort skipped (more than SORT_SMEM_MAX matches).
+__global__ void __launch_bounds__(256) k_match_sort_big(const __grid_constant__ MatchPlan P, int32_t* __restrict__ match_out,
+                                                        float* __restrict__ conf_out) {
+    __shared__ unsigned long long s_k[256];
+    const int p = P.p0 + blockIdx.y;
+    const int n = P.mcount[p];
+    if (n <= SORT_SMEM_MAX || (int)blockIdx.x * 256 >= n) return;
     const unsigned long long* keys = P.mkeys + (size_t)p * P.nmax;
     const int e = blockIdx.x * 256 + threadIdx.x;
     const unsigned long long mine = (e < n) ? keys[e] : 0ull;
@@ -631,10 +843,28 @@ static int run_match_chunk(SfmCtx* ctx, cudaStream_t s, MatchPlan P, int p0, int
         SFM_LAUNCH(ctx, s, "k_flag_all", k_flag_all<<<rowgrid, 256, 0, s>>>(P));
     }
     SFM_LAUNCH(ctx, s, "k_work_scan", k_work_scan<<<1, 32, 0, s>>>(P));
-    SFM_LAUNCH(ctx, s, "k_match_exact", k_match_exact<<<2 * ctx->sm_count, 256, 0, s>>>(P));
+    // persistent grids: exactly the CTAs that are resident at once (a second wave would start on items
+    // the first one has already walked past)
+    int per_sm = 1;
+    if (P.mode == SFM_MATCH_AUTO) {
+        SFM_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_rescan, 256, 0));
+        SFM_LAUNCH(ctx, s, "k_match_rescan", k_match_rescan<<<std::max(per_sm, 1) * ctx->sm_count, 256, 0, s>>>(P));
+    } else {
+        SFM_CUDA_CHECK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_match_exact, 256, 0));
+        SFM_LAUNCH(ctx, s, "k_match_exact", k_match_exact<<<std::max(per_sm, 1) * ctx->sm_count, 256, 0, s>>>(P));
+    }
     SFM_LAUNCH(ctx, s, "k_match_merge", k_match_merge<<<rowgrid, 256, 0, s>>>(P));
     SFM_LAUNCH(ctx, s, "k_match_emit", k_match_emit<<<rowgrid, 256, 0, s>>>(P));
-    SFM_LAUNCH(ctx, s, "k_match_sort", k_match_sort<<<rowgrid, 256, 0, s>>>(P, match_out, conf_out, count_out, stats_out));
+    {
+        int n2pow = 32;
+        while (n2pow < P.nmax && n2pow < SORT_SMEM_MAX) n2pow <<= 1;
+        const int smem = n2pow * (int)sizeof(unsigned long long);
+        SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        SFM_LAUNCH(ctx, s, "k_match_sort", k_match_sort<<<pn, n2pow >= 2048 ? 1024 : 256, smem, s>>>(
+                                               P, n2pow, match_out, conf_out, count_out, stats_out));
+        if (P.nmax > SORT_SMEM_MAX)
+            SFM_LAUNCH(ctx, s, "k_match_sort_big", k_match_sort_big<<<rowgrid, 256, 0, s>>>(P, match_out, conf_out));
+    }
     return SFM_OK;
 }
 
@@ -651,6 +881,12 @@ static int run_match(SfmCtx* ctx, cudaStream_t st, MatchPlan& P, const MatchWs& 
     // streams so the re-check of one chunk overlaps the tensor-core pass of the next buys nothing --
     // both are bound by the same L2 -> SM bandwidth: 2.10 ms either way for 66 pairs of 8192 x 8192.)
     return run_match_chunk(ctx, st, P, 0, P.n_pairs, 0, match_out, conf_out, count_out, stats_out);
+}
+
+// development knob: SFM_MATCH_NO_PRUNE=1 re-checks every row (measures what the ratio prune saves)
+static int match_no_prune() {
+    static const int v = [] { const char* e = getenv("SFM_MATCH_NO_PRUNE"); return (e && e[0] == '1') ? 1 : 0; }();
+    return v;
 }
 
 extern "C" {
@@ -686,7 +922,7 @@ int sfm_match_ratio(SfmCtx* ctx, void* stream, const float* f1_dev, int n1, cons
     if (cap < 1) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "cap < 1");
     match_bind(P, ws, workspace_dev);
     P.f1 = f1_dev; P.f2 = f2_dev; P.n1 = n1; P.n2 = n2;
-    P.thr = ratio_threshold; P.mode = mode; P.cap = cap;
+    P.thr = ratio_threshold; P.mode = mode; P.cap = cap; P.no_prune = match_no_prune();
     return run_match(ctx, (cudaStream_t)stream, P, ws, workspace_dev, match_out, conf_out, count_out, nullptr);
 }
 
@@ -710,7 +946,7 @@ int sfm_match_ratio_batch(SfmCtx* ctx, void* stream, const float* desc_dev, cons
     if (cap < 1) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "cap < 1");
     match_bind(P, ws, workspace_dev);
     P.desc = desc_dev; P.counts_in = counts_dev; P.pairs_in = pairs_dev;
-    P.thr = ratio_threshold; P.mode = mode; P.cap = cap;
+    P.thr = ratio_threshold; P.mode = mode; P.cap = cap; P.no_prune = match_no_prune();
     return run_match(ctx, (cudaStream_t)stream, P, ws, workspace_dev, match_out, conf_out, count_out, stats_out);
 }
 

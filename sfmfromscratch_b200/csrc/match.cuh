@@ -20,7 +20,7 @@ constexpr int MT_MAX_CHUNKS = 4;       // pair chunks overlapped on two internal
 
 struct MatchPlan {
     int n_sets, nmax, nmax_pad, n_pairs;
-    int p0, pn, woff, pad_;           // pair chunk [p0, p0+pn) this launch covers; its slot in work_off
+    int p0, pn, woff, no_prune;       // pair chunk [p0, p0+pn) this launch covers; its slot in work_off; knob
     int n_splits, tiles_per_split, n_tiles, n_lists;
     int n_xchunks;                    // exact-scan column chunks
     int mode, cap;
