@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "match.cuh"
 
@@ -128,33 +129,89 @@ __device__ __forceinline__ void top2_push(Top2& s, float d, int j) {
 // Cauchy-Schwarz on the residual norms, accumulation, index packing, and the
 // float32 rounding of the exact sum itself).  Uncertified rows go to the exact
 // scan.  NV = candidate entries per lane (ceil(n_lists * 4 / 8)).
-constexpr int RC_ROWS = 32;            // rows per CTA (256 threads)
+constexpr int RC_ROWS = 256;           // rows per CTA: phase 1 is thread per row
+constexpr int RC_TEAMS = 32;           // phase 2: 8-lane teams over the surviving rows
 constexpr int RC_SQ_STRIDE = SFM_DESC_DIM + 8;   // staging row of squares: 544 bytes keeps the 4 columns on distinct banks
 
+// Phase 1 (thread per row): the row's error bound and the ratio prune.  k0 <= k1 are the two
+// smallest group keys, so the nearest exact distance is at least L0 = k0 + |a|^2 - E and the
+// second-nearest (two distinct columns exist that close) at most U1 = k1 + |a|^2 + E.  When
+// sqrt(L0 / U1) exceeds the threshold with room for the two float32 roundings of sqrt and divide,
+// the reference's ratio test rejects the row whatever the exact values are: nothing is gathered
+// (d1 = 0 makes k_match_emit skip the row).  Surviving rows are compacted so that phase 2 runs
+// with full teams.
+// Phase 2 (8 lanes per row): as described above.
 template <int NV>
 __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant__ MatchPlan P) {
     extern __shared__ __align__(16) unsigned char rc_smem[];
-    float (*s_sq)[MT_GROUP][RC_SQ_STRIDE] = reinterpret_cast<float (*)[MT_GROUP][RC_SQ_STRIDE]>(rc_smem);
-    __shared__ int s_visited;
+    float (*s_sq)[MT_SUB][RC_SQ_STRIDE] = reinterpret_cast<float (*)[MT_SUB][RC_SQ_STRIDE]>(rc_smem);
+    __shared__ double s_ebase[RC_ROWS], s_na[RC_ROWS];
+    __shared__ int16_t s_rows[RC_ROWS];
+    __shared__ int s_n, s_visited;
     const int p = P.p0 + blockIdx.y;
+    const int qa = P.pairs[2 * p], qb = P.pairs[2 * p + 1];
+    const int n1 = P.set_cnt[qa], n2 = P.set_cnt[qb];
+    if (n2 < 2) return;                                    // the pair emits nothing
+    const int E = P.n_lists * MT_TOPK;
+    const double q_rel = 1.1 / 8192.0 * 2.0;               // packing drops 10 mantissa bits
+    if (threadIdx.x == 0) { s_n = 0; s_visited = 0; }
+    __syncthreads();
+    {
+        const int row = blockIdx.x * RC_ROWS + threadIdx.x;
+        if (row < n1) {
+            const uint4* l4 = reinterpret_cast<const uint4*>(P.cands + ((size_t)p * P.nmax_pad + row) * (size_t)E);
+            float k0 = INFINITY, k1 = INFINITY;
+            for (int e = 0; e < E / 4; ++e) {
+                const uint4 q = l4[e];
+                const uint32_t pk[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float v = __uint_as_float(pk[i] & ~MT_IDX_MASK);
+                    if (v < MT_INVALID) {
+                        if (v < k0) { k1 = k0; k0 = v; } else if (v < k1) k1 = v;
+                    }
+                }
+            }
+            const size_t arow = (size_t)qa * P.nmax_pad + row;
+            const double na = (double)P.nb[arow];
+            const double hat_a = (double)P.hatn[arow], res_a = (double)P.resn[arow];
+            const double mh = (double)P.setmax[4 * qb + 0], mr = (double)P.setmax[4 * qb + 1], mnb = (double)P.setmax[4 * qb + 2];
+            const double e_fp16 = 2.0 * (hat_a * mr + res_a * mh + res_a * mr);
+            const double e_acc = 2.0 * hat_a * mh * (1.0 / 262144.0);                   // 2^-18
+            const double e_ref = (na + mnb + 2.0 * sqrt(na * mnb)) * (1.0 / 524288.0);  // 2^-19 * dmax^2
+            const double e_nrm = (na + mnb) * (1.0 / 131072.0);                         // 2^-17
+            const double e_base = 1.1 * (e_fp16 + e_acc + e_ref + e_nrm) + 1e-12;
+            bool pruned = false;
+            if (k1 < INFINITY && P.thr >= 0.0f && !P.no_prune) {
+                const double em = e_base + q_rel * fmax(fabs((double)k0), fabs((double)k1));
+                const double L0 = (double)k0 + na - em, U1 = (double)k1 + na + em;
+                pruned = L0 > 0.0 && L0 * (1.0 - 4e-6) > (double)P.thr * (double)P.thr * U1;
+            }
+            if (pruned) {
+                const size_t o = (size_t)p * P.nmax + row;
+                P.res_idx[o] = -1; P.res_d0[o] = 0.f; P.res_d1[o] = 0.f;
+            } else {
+                const int slot = atomicAdd(&s_n, 1);
+                s_rows[slot] = (int16_t)threadIdx.x; s_ebase[slot] = e_base; s_na[slot] = na;
+            }
+        }
+    }
+    __syncthreads();
+    const int n_live = s_n;
     const int team = threadIdx.x >> 3, j = threadIdx.x & 7;
     const int c = j & 3, h = j >> 2;
     const unsigned tmask = 0xffu << (threadIdx.x & 24);
-    const int row = blockIdx.x * RC_ROWS + team;
-    const int qa = P.pairs[2 * p], qb = P.pairs[2 * p + 1];
-    const int n1 = P.set_cnt[qa], n2 = P.set_cnt[qb];
-    if (threadIdx.x == 0) s_visited = 0;
-    __syncthreads();
+    const float* B = P.set_ptr[qb];
     int visited = 0;
-    if (row < n1 && n2 >= 2) {                             // n2 < 2: the pair emits nothing
-        const float* B = P.set_ptr[qb];
+    for (int slot = team; slot < n_live; slot += RC_TEAMS) {
+        const int row = blockIdx.x * RC_ROWS + (int)s_rows[slot];
+        const double e_base = s_ebase[slot], na = s_na[slot];
         float4 a4[4];                                      // elements 32 i + 4 j .. + 3 of the query row
         {
             const float4* A4 = reinterpret_cast<const float4*>(P.set_ptr[qa] + (size_t)row * SFM_DESC_DIM);
 #pragma unroll
             for (int i = 0; i < 4; ++i) a4[i] = A4[j + 8 * i];
         }
-        const int E = P.n_lists * MT_TOPK;
         const uint32_t* lists = P.cands + ((size_t)p * P.nmax_pad + row) * (size_t)E;
         float val[NV];
         uint32_t code[NV];
@@ -175,17 +232,6 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
         }
 #pragma unroll
         for (int o = 4; o > 0; o >>= 1) Lmin = fminf(Lmin, __shfl_xor_sync(tmask, Lmin, o, 8));
-
-        const size_t arow = (size_t)qa * P.nmax_pad + row;
-        const double na = (double)P.nb[arow];
-        const double hat_a = (double)P.hatn[arow], res_a = (double)P.resn[arow];
-        const double mh = (double)P.setmax[4 * qb + 0], mr = (double)P.setmax[4 * qb + 1], mnb = (double)P.setmax[4 * qb + 2];
-        const double e_fp16 = 2.0 * (hat_a * mr + res_a * mh + res_a * mr);
-        const double e_acc = 2.0 * hat_a * mh * (1.0 / 262144.0);                   // 2^-18
-        const double e_ref = (na + mnb + 2.0 * sqrt(na * mnb)) * (1.0 / 524288.0);  // 2^-19 * dmax^2
-        const double e_nrm = (na + mnb) * (1.0 / 131072.0);                         // 2^-17
-        const double e_base = 1.1 * (e_fp16 + e_acc + e_ref + e_nrm) + 1e-12;
-        const double q_rel = 1.1 / 8192.0 * 2.0;                                    // packing drops 10 mantissa bits
 
         Top2 best = {INFINITY, -1, INFINITY};
 
@@ -214,22 +260,22 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
         auto group_col = [&](uint32_t wc) -> int {
             const int list = (int)(wc >> MT_IDX_BITS);
             const int split = list >> 1, half = list & 1;
-            const int tile = split * P.tiles_per_split + (int)((wc & MT_IDX_MASK) >> 4);
-            return tile * MT_COLS + half * 64 + (int)(wc & 15u) * MT_GROUP;
+            const int tile = split * P.tiles_per_split + (int)((wc & MT_IDX_MASK) >> MT_GROUP_BITS);
+            return tile * MT_COLS + half * (MT_COLS / 2) + (int)(wc & (MT_GROUPS_PER_HALF - 1)) * MT_GROUP;
         };
-        // the group's 4 columns as full lines: v[4 cc + i] = elements 32 i + 4 j .. + 3 of column col0 + cc
+        // 4 columns as full lines: v[4 cc + i] = elements 32 i + 4 j .. + 3 of column col0 + cc
         auto group_load = [&](int col0, float4 (&v)[16]) {
 #pragma unroll
-            for (int cc = 0; cc < MT_GROUP; ++cc) {
+            for (int cc = 0; cc < MT_SUB; ++cc) {
                 const float4* bp = reinterpret_cast<const float4*>(B + (size_t)min(col0 + cc, n2 - 1) * SFM_DESC_DIM) + j;
 #pragma unroll
                 for (int i = 0; i < 4; ++i) v[4 * cc + i] = bp[8 * i];
             }
         };
-        // squares (a - b)^2 of a loaded group into the team's staging rows, in the columns' own element order
+        // squares (a - b)^2 of the loaded columns into the team's staging rows, in the columns' own element order
         auto stage_squares = [&](const float4 (&v)[16]) {
 #pragma unroll
-            for (int cc = 0; cc < MT_GROUP; ++cc)
+            for (int cc = 0; cc < MT_SUB; ++cc)
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float4 b = v[4 * cc + i], a = a4[i];
@@ -253,78 +299,62 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
                 x.x = __fadd_rn(x.x, y.x); x.y = __fadd_rn(x.y, y.y);
                 x.z = __fadd_rn(x.z, y.z); x.w = __fadd_rn(x.w, y.w);
             }
-            __syncwarp(tmask);                                                  // staging rows are reused by the next group
+            __syncwarp(tmask);                                                  // staging rows are reused by the next sub-group
             const float s4 = __fadd_rn(__fadd_rn(x.x, x.y), __fadd_rn(x.z, x.w));   // (r0+r1)+(r2+r3) or (r4+r5)+(r6+r7)
             return __fadd_rn(s4, __shfl_xor_sync(tmask, s4, 4, 8));
         };
-        auto push_group = [&](float d2, int col0) {
+        auto push_sub = [&](float d2, int col0) {
 #pragma unroll
-            for (int tm = 0; tm < MT_GROUP; ++tm) {
+            for (int tm = 0; tm < MT_SUB; ++tm) {
                 const float dd = __shfl_sync(tmask, d2, tm, 8);
                 if (col0 + tm < n2) top2_push(best, dd, col0 + tm);
             }
-            ++visited;
+        };
+        // NG candidate groups, MT_SUB columns at a time; the next sub-group's loads are issued once the
+        // current one's registers are free and fly under its summation
+        auto visit = [&](const int (&cols)[2], auto ng_tag) {
+            constexpr int SPG = MT_GROUP / MT_SUB;
+            constexpr int NS = decltype(ng_tag)::value * SPG;
+            float4 v[16];
+            group_load(cols[0], v);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) {
+                const int cur = cols[i / SPG] + (i % SPG) * MT_SUB;
+                stage_squares(v);
+                if (i + 1 < NS) group_load(cols[(i + 1) / SPG] + ((i + 1) % SPG) * MT_SUB, v);
+                push_sub(sum_staged(), cur);
+            }
+            visited += decltype(ng_tag)::value;
         };
 
-        // The two best entries are evaluated together (their loads overlap): the second one is needed
-        // in practice anyway, because four columns rarely certify a row.
+        // The two best entries are evaluated together: the second one is needed in practice anyway,
+        // because one group rarely certifies a row.
         float wv; int wl, bi; uint32_t bc;
         find_min(wv, wl, bi, bc);
-        bool done = false;                                         // result already written (pruned row)
         if (wl < 8) {
-            const float k0 = wv;
-            const int col1 = group_col(consume(wl, bi, bc));
+            int cols[2];
+            cols[0] = group_col(consume(wl, bi, bc));
             find_min(wv, wl, bi, bc);
-            // Ratio prune.  k0 <= k1 are the two smallest group keys, so the nearest exact distance is at
-            // least L0 = k0 + |a|^2 - E and the second-nearest (two distinct columns exist that close) at
-            // most U1 = k1 + |a|^2 + E.  When sqrt(L0 / U1) exceeds the threshold with room for the two
-            // float32 roundings of sqrt and divide, the reference's ratio test rejects the row whatever
-            // the exact values are: nothing is gathered (d1 = 0 makes k_match_emit skip the row).
-            bool pruned = false;
-            if (wl < 8 && P.thr >= 0.0f && !P.no_prune) {
-                const double em = e_base + q_rel * fmax(fabs((double)k0), fabs((double)wv));
-                const double L0 = (double)k0 + na - em, U1 = (double)wv + na + em;
-                pruned = L0 > 0.0 && L0 * (1.0 - 4e-6) > (double)P.thr * (double)P.thr * U1;
-            }
-            if (pruned) {
-                done = true;
-                if (j == 0) {
-                    const size_t o = (size_t)p * P.nmax + row;
-                    P.res_idx[o] = -1; P.res_d0[o] = 0.f; P.res_d1[o] = 0.f;
-                }
-            } else if (wl < 8) {
-                const int col2 = group_col(consume(wl, bi, bc));
-                // the second group's loads are issued once the first one's registers are free and fly
-                // under its summation
-                float4 v[16];
-                group_load(col1, v);
-                stage_squares(v);
-                group_load(col2, v);
-                push_group(sum_staged(), col1);
-                stage_squares(v);
-                push_group(sum_staged(), col2);
+            if (wl < 8) {
+                cols[1] = group_col(consume(wl, bi, bc));
+                visit(cols, std::integral_constant<int, 2>{});
             } else {
-                float4 v[16];
-                group_load(col1, v);
-                stage_squares(v);
-                push_group(sum_staged(), col1);
+                cols[1] = cols[0];
+                visit(cols, std::integral_constant<int, 1>{});
             }
-            while (!done) {
+            for (;;) {
                 find_min(wv, wl, bi, bc);
                 if (wl >= 8) break;                               // nothing left
                 const double bound = (double)wv + na - (e_base + q_rel * fabs((double)wv));
                 if (bound > (double)best.d1) break;               // the rest cannot matter
-                const int col = group_col(consume(wl, bi, bc));
-                float4 v[16];
-                group_load(col, v);
-                stage_squares(v);
-                push_group(sum_staged(), col);
+                cols[0] = cols[1] = group_col(consume(wl, bi, bc));
+                visit(cols, std::integral_constant<int, 1>{});
             }
         }
         const bool certified =
             (Lmin == INFINITY) ||
             ((double)Lmin + na - (e_base + q_rel * fabs((double)Lmin)) > (double)best.d1);
-        if (j == 0 && !done) {
+        if (j == 0) {
             const size_t o = (size_t)p * P.nmax + row;
             if (certified) {
                 P.res_idx[o] = best.i0; P.res_d0[o] = best.d0; P.res_d1[o] = best.d1;
@@ -334,16 +364,18 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
                 P.res_d1[o] = best.d1;                            // upper bound of the true second-nearest: the rescan's filter
             }
         }
-        if (j == 0 && P.stats) atomicAdd(&s_visited, visited);
     }
-    __syncthreads();
-    if (threadIdx.x == 0 && P.stats && s_visited) atomicAdd(&P.stats[2 * p + 1], s_visited);
+    if (P.stats) {
+        if (j == 0 && visited) atomicAdd(&s_visited, visited);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_visited) atomicAdd(&P.stats[2 * p + 1], s_visited);
+    }
 }
 
 static int launch_match_recheck(SfmCtx* ctx, cudaStream_t s, const MatchPlan& P) {
     const dim3 grid(ceil_div(P.nmax, RC_ROWS), P.pn);
     const int nv = ceil_div(P.n_lists * MT_TOPK, 8);
-    constexpr int smem = RC_ROWS * MT_GROUP * RC_SQ_STRIDE * (int)sizeof(float);
+    constexpr int smem = RC_TEAMS * MT_SUB * RC_SQ_STRIDE * (int)sizeof(float);
 #define RC_GO(NV)                                                                                          \
     do {                                                                                                   \
         SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_recheck<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \

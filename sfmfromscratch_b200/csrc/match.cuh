@@ -6,10 +6,13 @@
 
 constexpr int MT_ROWS = 256;          // query rows per work unit (two M=128 MMA row tiles)
 constexpr int MT_COLS = 128;          // train columns per MMA tile (UMMA N)
-constexpr int MT_MAX_TILES = 64;      // column tiles per split (6 bits of the packed index)
 constexpr int MT_GROUP = 4;           // columns per candidate group
+constexpr int MT_SUB = 4;             // columns the re-check evaluates at a time (MT_GROUP is a multiple)
+constexpr int MT_GROUPS_PER_HALF = (MT_COLS / 2) / MT_GROUP;
+constexpr int MT_GROUP_BITS = MT_GROUPS_PER_HALF == 32 ? 5 : (MT_GROUPS_PER_HALF == 16 ? 4 : 3);
 constexpr int MT_TOPK = 4;            // candidate groups kept per list
-constexpr int MT_IDX_BITS = 10;       // tile_local (6) | group within 64 columns (4)
+constexpr int MT_IDX_BITS = 10;       // packed into the low mantissa bits of a key: tile_local << MT_GROUP_BITS | group within the list's half tile
+constexpr int MT_MAX_TILES = 1 << (MT_IDX_BITS - MT_GROUP_BITS);   // column tiles per split
 constexpr uint32_t MT_IDX_MASK = (1u << MT_IDX_BITS) - 1u;
 constexpr float MT_SENTINEL = 1.0e30f;   // norm term of padding rows: never a candidate
 constexpr float MT_INVALID = 1.0e29f;    // packed values >= this are empty slots
