@@ -5,8 +5,8 @@
 #include "common.cuh"
 
 constexpr int MT_ROWS = 256;          // query rows per work unit (two M=128 MMA row tiles)
-constexpr int MT_COLS = 128;          // train columns per MMA tile (UMMA N)
-constexpr int MT_GROUP = 4;           // columns per candidate group
+constexpr int MT_COLS = 256;          // train columns per MMA tile (UMMA N)
+constexpr int MT_GROUP = 8;           // columns per candidate group
 constexpr int MT_SUB = 4;             // columns the re-check evaluates at a time (MT_GROUP is a multiple)
 constexpr int MT_GROUPS_PER_HALF = (MT_COLS / 2) / MT_GROUP;
 constexpr int MT_GROUP_BITS = MT_GROUPS_PER_HALF == 32 ? 5 : (MT_GROUPS_PER_HALF == 16 ? 4 : 3);

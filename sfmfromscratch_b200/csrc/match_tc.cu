@@ -2,17 +2,25 @@
 //
 // For a work unit (pair, 256 query rows, column split) the CTA computes the
 // 256 x N tile products  acc = A16 * B16^T  on the 5th-generation tensor cores
-// (fp16 inputs, fp32 accumulation in TMEM, two M=128 x N=128 x K=16 UMMA chains
-// per 128-column tile), and the epilogue warps turn each accumulator straight
-// into the ranking key  |b|^2 - 2 a.b  and keep, per query row, the 4 smallest
-// groups of 4 columns.  The distance matrix never leaves TMEM / registers; the
-// only global output is 16 bytes per (row, list).
+// (fp16 inputs, fp32 accumulation in TMEM), 256 train columns at a time: per
+// column tile one M=128 x N=256 x K=16 UMMA chain for each of the two 128-row
+// halves of the unit, each into its own 256-column TMEM accumulator.  N = 256
+// is what keeps the tensor pipe fed: both operands come from shared memory, and
+// an M128 N128 K16 instruction reads 8 KB per 64 cycles -- all of the 128 B/clk
+// the SM's shared memory has, with the TMA fill and the epilogue still to
+// serve -- while N256 reads 12 KB per 128 cycles.  The two accumulators double
+// as the pipeline: the epilogue drains half 0 while the tensor pipe works on
+// half 1 of the same column tile, and vice versa.
+// The epilogue warps turn each accumulator straight into the ranking key
+// |b|^2 - 2 a.b  and keep, per query row, the 4 smallest groups of MT_GROUP
+// columns.  The distance matrix never leaves TMEM / registers; the only global
+// output is 16 bytes per (row, list).
 //
 // Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator +
 // single-thread MMA issuer, warps 2..9 = epilogue (TMEM lane quarter = warp % 4,
-// column half = (warp - 2) / 4).
+// column half of the 256-wide tile = (warp - 2) / 4).
 // Pipelines: smem ring full/empty (TMA <-> MMA), A-tile full/empty per unit,
-// TMEM accumulator ring full/empty (MMA <-> epilogue).
+// TMEM accumulator full/empty per row half (MMA <-> epilogue).
 #include <cuda.h>
 
 #include "match.cuh"
@@ -20,13 +28,15 @@
 namespace {
 
 constexpr int TC_THREADS = 320;
-constexpr int TC_STAGES = 3;                       // B smem ring
-constexpr int TC_ACC = 2;                          // TMEM accumulator ring (2 x 256 columns)
+constexpr int TC_STAGES = 2;                       // B smem ring
+constexpr int TC_ACC = 2;                          // TMEM accumulators: one per 128-row half of the unit (256 columns each)
 constexpr int TC_KBLK = 64;                        // fp16 elements per 128-byte swizzle row
 constexpr uint32_t TC_SUB_BYTES = 128 * 128;       // one [128 rows][64 halves] box = 16 KB
 constexpr uint32_t TC_A_BYTES = 4 * TC_SUB_BYTES;  // 2 row tiles x 2 k-blocks
-constexpr uint32_t TC_B_BYTES = 2 * TC_SUB_BYTES;  // 2 k-blocks
-constexpr uint32_t TC_NB_BYTES = 8 * 2 * 64 * 4;   // per epilogue warp: 2 buffers of 64 norms
+constexpr uint32_t TC_B_BYTES = 4 * TC_SUB_BYTES;  // 2 k-blocks x [256 rows][64 halves] (two boxes each)
+constexpr int TC_HALF = MT_COLS / 2;               // columns per epilogue warp and tile
+constexpr uint32_t TC_NB_BYTES = 8 * 2 * TC_HALF * 4;   // per epilogue warp: 2 buffers of 128 norms
+static_assert(MT_COLS == 256 && MT_ROWS == 256, "tile geometry");
 constexpr uint32_t TC_SMEM = 1024 + TC_A_BYTES + TC_STAGES * TC_B_BYTES + TC_NB_BYTES + 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -82,7 +92,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
           "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
         : "r"(taddr));
 }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld names the registers of the load it completes, so that nothing that reads them is scheduled above it
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.wait::ld.sync.aligned;"
+        : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+          "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+          "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+          "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+        :
+        : "memory");
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
 // start address >> 4 in [0,14), LBO (unused for swizzled K-major, 1) in [16,30),
@@ -186,8 +206,12 @@ k_match_tc(const __grid_constant__ MatchPlan P, const __grid_constant__ CUtensor
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     mbar_expect_tx(bar_full + 8 * stage, TC_B_BYTES);
                     const int brow = u.qb * P.nmax_pad + t * MT_COLS;
-                    tma_load_2d(sB + stage * TC_B_BYTES, &tmap, bar_full + 8 * stage, 0, brow);
-                    tma_load_2d(sB + stage * TC_B_BYTES + TC_SUB_BYTES, &tmap, bar_full + 8 * stage, TC_KBLK, brow);
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                        for (int rh = 0; rh < 2; ++rh)
+                            tma_load_2d(sB + stage * TC_B_BYTES + (kb * 2 + rh) * TC_SUB_BYTES, &tmap, bar_full + 8 * stage,
+                                        kb * TC_KBLK, brow + rh * 128);
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -195,42 +219,42 @@ k_match_tc(const __grid_constant__ MatchPlan P, const __grid_constant__ CUtensor
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer (one thread)
         if (lane == 0) {
-            int stage = 0, acc = 0; uint32_t phase = 0, accphase = 0, aphase = 0;
+            int stage = 0; uint32_t phase = 0, accphase = 0, aphase = 0;
             for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
                 const UnitInfo u = decode_unit(P, unit);
                 if (!u.active || u.t0 >= u.t1) continue;
                 mbar_wait(bar_afull, aphase);
                 aphase ^= 1;
                 for (int t = u.t0; t < u.t1; ++t) {
-                    mbar_wait(bar_tempty + 8 * acc, accphase ^ 1);
                     mbar_wait(bar_full + 8 * stage, phase);
-                    tc_fence_after();
 #pragma unroll
                     for (int rt = 0; rt < 2; ++rt) {
-                        const uint32_t d = tmem_base + (uint32_t)(acc * 256 + rt * 128);
+                        mbar_wait(bar_tempty + 8 * rt, accphase ^ 1);
+                        tc_fence_after();
+                        const uint32_t d = tmem_base + (uint32_t)(rt * MT_COLS);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            const uint32_t koff = (uint32_t)(k >> 2) * TC_SUB_BYTES + (uint32_t)(k & 3) * 32u;
-                            const uint64_t ad = umma_desc(sA + (uint32_t)rt * 2u * TC_SUB_BYTES + koff);
-                            const uint64_t bd = umma_desc(sB + (uint32_t)stage * TC_B_BYTES + koff);
+                            const uint64_t ad = umma_desc(sA + (uint32_t)(rt * 2 + (k >> 2)) * TC_SUB_BYTES + (uint32_t)(k & 3) * 32u);
+                            const uint64_t bd = umma_desc(sB + (uint32_t)stage * TC_B_BYTES + (uint32_t)(k >> 2) * 2u * TC_SUB_BYTES +
+                                                          (uint32_t)(k & 3) * 32u);
                             tc_mma_f16(d, ad, bd, TC_IDESC, k > 0 ? 1u : 0u);
                         }
+                        tc_commit(bar_tfull + 8 * rt);             // this half's accumulator is ready for the epilogue
                     }
-                    tc_commit(bar_empty + 8 * stage);          // smem stage free once these MMAs retire
-                    tc_commit(bar_tfull + 8 * acc);            // accumulators ready for the epilogue
+                    tc_commit(bar_empty + 8 * stage);              // smem stage free once both halves' MMAs retire
                     if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-                    if (++acc == TC_ACC) { acc = 0; accphase ^= 1; }
+                    accphase ^= 1;
                 }
-                tc_commit(bar_aempty);                         // A tile free for the next unit
+                tc_commit(bar_aempty);                             // A tile free for the next unit
             }
         }
     } else {
         // ------------------------------------------------ epilogue warps
         const int ew = warp - 2;
         const int q = warp & 3;                                // TMEM lane quarter this warp may read
-        const int half = ew >> 2;                              // column half of every 128-column tile
-        float* my_nb = s_nb + ew * 128;                        // 2 buffers x 64 floats
-        int acc = 0; uint32_t accphase = 0;
+        const int half = ew >> 2;                              // column half of every 256-column tile
+        float* my_nb = s_nb + ew * (2 * TC_HALF);              // 2 buffers x 128 floats
+        uint32_t accphase = 0;
         for (int unit = blockIdx.x; unit < n_units; unit += gridDim.x) {
             const UnitInfo u = decode_unit(P, unit);
             if (!u.active) continue;
@@ -239,53 +263,67 @@ k_match_tc(const __grid_constant__ MatchPlan P, const __grid_constant__ CUtensor
             for (int rt = 0; rt < 2; ++rt)
 #pragma unroll
                 for (int e = 0; e < 4; ++e) m[rt][e] = 3.0e38f;
-            const float* nbrow = P.nb + (size_t)u.qb * P.nmax_pad;
+            const float* nbrow = P.nb + (size_t)u.qb * P.nmax_pad + half * TC_HALF + lane;
             int buf = 0;
-            float pre0 = 0.f, pre1 = 0.f;
+            float pre[4] = {0.f, 0.f, 0.f, 0.f};
             if (u.t0 < u.t1) {
-                pre0 = nbrow[u.t0 * MT_COLS + half * 64 + lane];
-                pre1 = nbrow[u.t0 * MT_COLS + half * 64 + 32 + lane];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pre[i] = nbrow[u.t0 * MT_COLS + 32 * i];
             }
             for (int t = u.t0; t < u.t1; ++t) {
-                float* nbs = my_nb + buf * 64;
-                nbs[lane] = pre0; nbs[32 + lane] = pre1;
+                float* nbs = my_nb + buf * TC_HALF;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) nbs[lane + 32 * i] = pre[i];
                 __syncwarp();
                 if (t + 1 < u.t1) {                             // prefetch the next tile's norms
-                    pre0 = nbrow[(t + 1) * MT_COLS + half * 64 + lane];
-                    pre1 = nbrow[(t + 1) * MT_COLS + half * 64 + 32 + lane];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) pre[i] = nbrow[(t + 1) * MT_COLS + 32 * i];
                 }
-                mbar_wait(bar_tfull + 8 * acc, accphase);
-                tc_fence_after();
-                const uint32_t tile_local = (uint32_t)(t - u.t0);
+                const uint32_t tile_bits = (uint32_t)(t - u.t0) << MT_GROUP_BITS;
+                // 32 accumulator columns -> 32 / MT_GROUP candidate groups of row (q, lane) of half rt
+                auto process = [&](const uint32_t (&v)[32], int rt, int c) {
+#pragma unroll
+                    for (int g = 0; g < 32 / MT_GROUP; ++g) {
+                        float gm = 3.0e38f;
+#pragma unroll
+                        for (int e = 0; e < MT_GROUP; e += 4) {
+                            const float4 nb4 = *reinterpret_cast<const float4*>(nbs + c * 32 + g * MT_GROUP + e);
+                            const float k0 = __fmaf_rn(__uint_as_float(v[MT_GROUP * g + e + 0]), -2.0f, nb4.x);
+                            const float k1 = __fmaf_rn(__uint_as_float(v[MT_GROUP * g + e + 1]), -2.0f, nb4.y);
+                            const float k2 = __fmaf_rn(__uint_as_float(v[MT_GROUP * g + e + 2]), -2.0f, nb4.z);
+                            const float k3 = __fmaf_rn(__uint_as_float(v[MT_GROUP * g + e + 3]), -2.0f, nb4.w);
+                            const float g4 = fminf(fminf(k0, k1), fminf(k2, k3));
+                            gm = (e == 0) ? g4 : fminf(gm, g4);
+                        }
+                        const uint32_t pk = (__float_as_uint(gm) & ~MT_IDX_MASK) | tile_bits | (uint32_t)(c * (32 / MT_GROUP) + g);
+                        top4_insert(m[rt], __uint_as_float(pk));
+                    }
+                };
 #pragma unroll
                 for (int rt = 0; rt < 2; ++rt) {
-#pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t v[32];
-                        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) +
-                                               (uint32_t)(acc * 256 + rt * 128 + half * 64 + c * 32);
-                        tc_ld32(taddr, v);
-                        tc_wait_ld();
-                        if (rt == 1 && c == 1) {                // all four loads of this stage are in registers
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-                        }
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            const float4 nb4 = *reinterpret_cast<const float4*>(nbs + c * 32 + g * 4);
-                            const float k0 = __fmaf_rn(__uint_as_float(v[4 * g + 0]), -2.0f, nb4.x);
-                            const float k1 = __fmaf_rn(__uint_as_float(v[4 * g + 1]), -2.0f, nb4.y);
-                            const float k2 = __fmaf_rn(__uint_as_float(v[4 * g + 2]), -2.0f, nb4.z);
-                            const float k3 = __fmaf_rn(__uint_as_float(v[4 * g + 3]), -2.0f, nb4.w);
-                            const float gm = fminf(fminf(k0, k1), fminf(k2, k3));
-                            const uint32_t pk = (__float_as_uint(gm) & ~MT_IDX_MASK) | (tile_local << 4) | (uint32_t)(c * 8 + g);
-                            top4_insert(m[rt], __uint_as_float(pk));
-                        }
-                    }
+                    mbar_wait(bar_tfull + 8 * rt, accphase);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(rt * MT_COLS + half * TC_HALF);
+                    uint32_t va[32], vb[32];
+                    // the next 32 columns are in flight while the current ones are ranked
+                    tc_ld32(taddr, va);
+                    tc_wait_ld(va);
+                    tc_ld32(taddr + 32, vb);
+                    process(va, rt, 0);
+                    tc_wait_ld(vb);
+                    tc_ld32(taddr + 64, va);
+                    process(vb, rt, 1);
+                    tc_wait_ld(va);
+                    tc_ld32(taddr + 96, vb);
+                    process(va, rt, 2);
+                    tc_wait_ld(vb);
+                    tc_fence_before();                          // this half's accumulator is in registers: hand it back
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * rt);
+                    process(vb, rt, 3);
                 }
                 buf ^= 1;
-                if (++acc == TC_ACC) { acc = 0; accphase ^= 1; }
+                accphase ^= 1;
             }
             // 16 bytes per (row, list)
             const int list = u.split * 2 + half;
