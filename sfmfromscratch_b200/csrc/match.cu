@@ -400,15 +400,32 @@ __global__ void k_flag_all(const __grid_constant__ MatchPlan P) {
     if (i == 0) P.flag_cnt[p] = n1;
 }
 
-__global__ void k_work_scan(const __grid_constant__ MatchPlan P) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    int acc = 0;
+// Exclusive prefix of the pairs' work-item counts (one CTA of 256 threads, chunks of 256 pairs).
+__global__ void __launch_bounds__(256) k_work_scan(const __grid_constant__ MatchPlan P) {
+    __shared__ int s_w[8];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int32_t* wo = P.work_off + P.woff;
-    for (int q = 0; q < P.pn; ++q) {
-        wo[q] = acc;
-        acc += ((P.flag_cnt[P.p0 + q] + MX_ROWS - 1) / MX_ROWS) * P.n_xchunks;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < P.pn; base += 256) {
+        const int q = base + threadIdx.x;
+        const int mine = (q < P.pn) ? ((P.flag_cnt[P.p0 + q] + MX_ROWS - 1) / MX_ROWS) * P.n_xchunks : 0;
+        int incl = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        int before = s_carry;
+        for (int w = 0; w < warp; ++w) before += s_w[w];
+        if (q < P.pn) wo[q] = before + incl - mine;
+        __syncthreads();
+        if (threadIdx.x == 255) s_carry = before + incl;
+        __syncthreads();
     }
-    wo[P.pn] = acc;
+    if (threadIdx.x == 0) wo[P.pn] = s_carry;
 }
 
 // Work item = (pair, 8 flagged rows, 1024-column chunk).  Each thread walks its
@@ -526,12 +543,123 @@ __global__ void __launch_bounds__(256, 1) k_match_exact(const __grid_constant__ 
 // transpose-reduction that leaves row r's dot product in the lanes whose bits 4..2 spell r.  Each
 // lane keeps the rows in the order i -> row i ^ (its bits 4..2), which makes "the half I send" the
 // same registers in every lane (no selects).
-constexpr int RS_UNROLL = 4;
+constexpr int RS_UNROLL = 6;
+
+// One work item with R (2, 4 or 8) query-row slots: most items carry one or two flagged rows, and the
+// dot products and the reduction scale with R.
+template <int R>
+__device__ __forceinline__ void rescan_item(const MatchPlan& P, int p, int rg, int ch, int qa, int qb, int n2, int nflag,
+                                            Top2* s_top /* [MX_ROWS] of this warp */) {
+    constexpr int LOG = (R == 8) ? 3 : (R == 4 ? 2 : 1);
+    constexpr unsigned HITMASK = (R == 8) ? 0x11111111u : (R == 4 ? 0x01010101u : 0x00010001u);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int myrow = lane >> (5 - LOG);
+    const int col0 = ch * MX_COLS;
+    const int col1 = min(col0 + MX_COLS, n2);
+    // the query rows (lane k: elements 4k..4k+3 of each; a[i] is row i ^ myrow), this lane's row norm and threshold
+    float4 a[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int slot = rg * MX_ROWS + (r ^ myrow);
+        a[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (slot < nflag) {
+            const int row = P.flag_rows[(size_t)p * P.nmax + slot];
+            a[r] = reinterpret_cast<const float4*>(P.set_ptr[qa] + (size_t)row * SFM_DESC_DIM)[lane];
+        }
+    }
+    float my_na = 0.f, my_T = -INFINITY;                   // empty slot: nothing passes the filter
+    {
+        const int slot = rg * MX_ROWS + myrow;
+        if (slot < nflag) {
+            const int row = P.flag_rows[(size_t)p * P.nmax + slot];
+            my_na = P.nb[(size_t)qa * P.nmax_pad + row];
+            const double mnb = (double)P.setmax[4 * qb + 2];
+            const double dn = (double)my_na, ab = sqrt(dn * mnb);
+            const double e = 1.1 * (ab * (1.0 / 65536.0) + (dn + mnb) * (1.0 / 262144.0) +
+                                    (dn + mnb + 2.0 * ab) * (1.0 / 524288.0)) + 1e-12;
+            // rounded up: the comparison below is in float32
+            my_T = __double2float_ru((double)P.res_d1[(size_t)p * P.nmax + row] + e);
+        }
+    }
+    const float* B = P.set_ptr[qb];
+    const float* nbq = P.nb + (size_t)qb * P.nmax_pad;
+
+    // rotating prefetch: RS_UNROLL columns in flight per warp, each slot refilled as soon as it is read
+    float4 buf[RS_UNROLL];
+    float buf_nb[RS_UNROLL];
+#pragma unroll
+    for (int u = 0; u < RS_UNROLL; ++u) {
+        const int jc = min(col0 + warp + 8 * u, n2 - 1);
+        buf[u] = reinterpret_cast<const float4*>(B + (size_t)jc * SFM_DESC_DIM)[lane];
+        buf_nb[u] = nbq[jc];
+    }
+    for (int jb = col0 + warp; jb < col1; jb += 8 * RS_UNROLL) {
+#pragma unroll
+        for (int u = 0; u < RS_UNROLL; ++u) {
+            const int jc = jb + 8 * u;
+            if (jc >= col1) break;                         // warp-uniform
+            const float4 b = buf[u];
+            const float b_nb = buf_nb[u];
+            {
+                const int jn = jc + 8 * RS_UNROLL;
+                if (jn < col1) {
+                    buf[u] = reinterpret_cast<const float4*>(B + (size_t)jn * SFM_DESC_DIM)[lane];
+                    buf_nb[u] = nbq[jn];
+                }
+            }
+            float d[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                d[r] = fmaf(a[r].w, b.w, fmaf(a[r].z, b.z, fmaf(a[r].y, b.y, a[r].x * b.x)));
+            // transpose-reduce: R rows x 32 lanes -> row (top LOG bits of the lane), summed over all lanes
+#pragma unroll
+            for (int half = R / 2, o = 16; half >= 1; half >>= 1, o >>= 1) {
+#pragma unroll
+                for (int r = 0; r < half; ++r) d[r] += __shfl_xor_sync(0xffffffffu, d[r + half], o);
+            }
+            float e1 = d[0];
+#pragma unroll
+            for (int o = 16 >> LOG; o > 0; o >>= 1) e1 += __shfl_xor_sync(0xffffffffu, e1, o);
+            const float approx = fmaf(-2.0f, e1, my_na + b_nb);
+            unsigned hits = __ballot_sync(0xffffffffu, approx <= my_T) & HITMASK;
+            while (hits) {                                 // rare: the reference's arithmetic for (row r, column jc)
+                const int src = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const int r = src >> (5 - LOG);
+                float4 av = a[0];                          // a[r ^ myrow] is row r
+#pragma unroll
+                for (int rr = 1; rr < R; ++rr) if (rr == (r ^ myrow)) av = a[rr];
+                // element 4k+q belongs to numpy's accumulator 4(k&1)+q at step k>>1: the running sums
+                // walk down the lanes two at a time
+                float tt;
+                float4 run;
+                tt = __fsub_rn(av.x, b.x); run.x = __fmul_rn(tt, tt);
+                tt = __fsub_rn(av.y, b.y); run.y = __fmul_rn(tt, tt);
+                tt = __fsub_rn(av.z, b.z); run.z = __fmul_rn(tt, tt);
+                tt = __fsub_rn(av.w, b.w); run.w = __fmul_rn(tt, tt);
+                const float4 sq = run;
+#pragma unroll 1
+                for (int m = 1; m < 16; ++m) {
+                    const float px = __shfl_up_sync(0xffffffffu, run.x, 2);
+                    const float py = __shfl_up_sync(0xffffffffu, run.y, 2);
+                    const float pz = __shfl_up_sync(0xffffffffu, run.z, 2);
+                    const float pw = __shfl_up_sync(0xffffffffu, run.w, 2);
+                    if ((lane >> 1) == m) {
+                        run.x = __fadd_rn(px, sq.x); run.y = __fadd_rn(py, sq.y);
+                        run.z = __fadd_rn(pz, sq.z); run.w = __fadd_rn(pw, sq.w);
+                    }
+                }
+                const float s4 = __fadd_rn(__fadd_rn(run.x, run.y), __fadd_rn(run.z, run.w));  // lane 30: (r0+r1)+(r2+r3), lane 31: (r4+r5)+(r6+r7)
+                const float d2 = __fadd_rn(__shfl_sync(0xffffffffu, s4, 30), __shfl_sync(0xffffffffu, s4, 31));
+                if (lane == 0) top2_push(s_top[r], d2, jc);
+            }
+        }
+    }
+}
 
 __global__ void __launch_bounds__(256, 2) k_match_rescan(const __grid_constant__ MatchPlan P) {
     __shared__ Top2 s_red[8][MX_ROWS];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int myrow = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
     const int32_t* wo = P.work_off + P.woff;
     const int total = wo[P.pn];
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
@@ -546,110 +674,13 @@ __global__ void __launch_bounds__(256, 2) k_match_rescan(const __grid_constant__
         const int qa = P.pairs[2 * p], qb = P.pairs[2 * p + 1];
         const int n2 = P.set_cnt[qb];
         const int nflag = P.flag_cnt[p];
-        const int col0 = ch * MX_COLS;
-        const int col1 = min(col0 + MX_COLS, n2);
-        // the eight query rows (lane k: elements 4k..4k+3 of each; a[i] is row i ^ myrow), this lane's row
-        // norm and threshold
-        float4 a[MX_ROWS];
-#pragma unroll
-        for (int r = 0; r < MX_ROWS; ++r) {
-            const int slot = rg * MX_ROWS + (r ^ myrow);
-            a[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (slot < nflag) {
-                const int row = P.flag_rows[(size_t)p * P.nmax + slot];
-                a[r] = reinterpret_cast<const float4*>(P.set_ptr[qa] + (size_t)row * SFM_DESC_DIM)[lane];
-            }
-        }
-        float my_na = 0.f, my_T = -INFINITY;                   // empty slot: nothing passes the filter
-        {
-            const int slot = rg * MX_ROWS + myrow;
-            if (slot < nflag) {
-                const int row = P.flag_rows[(size_t)p * P.nmax + slot];
-                my_na = P.nb[(size_t)qa * P.nmax_pad + row];
-                const double mnb = (double)P.setmax[4 * qb + 2];
-                const double dn = (double)my_na, ab = sqrt(dn * mnb);
-                const double e = 1.1 * (ab * (1.0 / 65536.0) + (dn + mnb) * (1.0 / 262144.0) +
-                                        (dn + mnb + 2.0 * ab) * (1.0 / 524288.0)) + 1e-12;
-                // rounded up: the comparison below is in float32
-                my_T = __double2float_ru((double)P.res_d1[(size_t)p * P.nmax + row] + e);
-            }
-        }
         __syncthreads();                                       // previous item's s_red has been read
         if (lane < MX_ROWS) s_red[warp][lane] = {INFINITY, -1, INFINITY};   // this warp's running top-2 per row (lane 0 updates)
         __syncwarp();
-        const float* B = P.set_ptr[qb];
-        const float* nbq = P.nb + (size_t)qb * P.nmax_pad;
-
-        float4 nxt[RS_UNROLL];
-        float nxt_nb[RS_UNROLL];
-        auto fetch = [&](int jbase) {
-#pragma unroll
-            for (int u = 0; u < RS_UNROLL; ++u) {
-                const int jc = min(jbase + 8 * u, n2 - 1);
-                nxt[u] = reinterpret_cast<const float4*>(B + (size_t)jc * SFM_DESC_DIM)[lane];
-                nxt_nb[u] = nbq[jc];
-            }
-        };
-        fetch(col0 + warp);
-        for (int jb = col0 + warp; jb < col1; jb += 8 * RS_UNROLL) {
-            float4 cur[RS_UNROLL];
-            float cur_nb[RS_UNROLL];
-#pragma unroll
-            for (int u = 0; u < RS_UNROLL; ++u) { cur[u] = nxt[u]; cur_nb[u] = nxt_nb[u]; }
-            if (jb + 8 * RS_UNROLL < col1) fetch(jb + 8 * RS_UNROLL);
-#pragma unroll
-            for (int u = 0; u < RS_UNROLL; ++u) {
-                const int jc = jb + 8 * u;
-                if (jc >= col1) break;                         // warp-uniform
-                const float4 b = cur[u];
-                float d[MX_ROWS];
-#pragma unroll
-                for (int r = 0; r < MX_ROWS; ++r)
-                    d[r] = fmaf(a[r].w, b.w, fmaf(a[r].z, b.z, fmaf(a[r].y, b.y, a[r].x * b.x)));
-                // transpose-reduce: 8 rows x 32 lanes -> row (bits 4..2 of the lane), summed over all lanes
-                float e4[4], e2[2], e1;
-#pragma unroll
-                for (int r = 0; r < 4; ++r) e4[r] = d[r] + __shfl_xor_sync(0xffffffffu, d[r + 4], 16);
-#pragma unroll
-                for (int r = 0; r < 2; ++r) e2[r] = e4[r] + __shfl_xor_sync(0xffffffffu, e4[r + 2], 8);
-                e1 = e2[0] + __shfl_xor_sync(0xffffffffu, e2[1], 4);
-                e1 += __shfl_xor_sync(0xffffffffu, e1, 2);
-                e1 += __shfl_xor_sync(0xffffffffu, e1, 1);
-                const float approx = fmaf(-2.0f, e1, my_na + cur_nb[u]);
-                unsigned hits = __ballot_sync(0xffffffffu, approx <= my_T) & 0x11111111u;
-                while (hits) {                                 // rare: the reference's arithmetic for (row r, column jc)
-                    const int src = __ffs(hits) - 1;
-                    hits &= hits - 1;
-                    const int r = ((src >> 4) & 1) * 4 + ((src >> 3) & 1) * 2 + ((src >> 2) & 1);
-                    float4 av = a[0];                      // a[r ^ myrow] is row r
-#pragma unroll
-                    for (int rr = 1; rr < MX_ROWS; ++rr) if (rr == (r ^ myrow)) av = a[rr];
-                    // element 4k+q belongs to numpy's accumulator 4(k&1)+q at step k>>1: the running sums
-                    // walk down the lanes two at a time
-                    float tt;
-                    float4 run;
-                    tt = __fsub_rn(av.x, b.x); run.x = __fmul_rn(tt, tt);
-                    tt = __fsub_rn(av.y, b.y); run.y = __fmul_rn(tt, tt);
-                    tt = __fsub_rn(av.z, b.z); run.z = __fmul_rn(tt, tt);
-                    tt = __fsub_rn(av.w, b.w); run.w = __fmul_rn(tt, tt);
-                    const float4 sq = run;
-#pragma unroll 1
-                    for (int m = 1; m < 16; ++m) {
-                        const float px = __shfl_up_sync(0xffffffffu, run.x, 2);
-                        const float py = __shfl_up_sync(0xffffffffu, run.y, 2);
-                        const float pz = __shfl_up_sync(0xffffffffu, run.z, 2);
-                        const float pw = __shfl_up_sync(0xffffffffu, run.w, 2);
-                        if ((lane >> 1) == m) {
-                            run.x = __fadd_rn(px, sq.x); run.y = __fadd_rn(py, sq.y);
-                            run.z = __fadd_rn(pz, sq.z); run.w = __fadd_rn(pw, sq.w);
-                        }
-                    }
-                    const float s4 = __fadd_rn(__fadd_rn(run.x, run.y), __fadd_rn(run.z, run.w));  // lane 30: (r0+r1)+(r2+r3), lane 31: (r4+r5)+(r6+r7)
-                    const float d2 = __fadd_rn(__shfl_sync(0xffffffffu, s4, 30), __shfl_sync(0xffffffffu, s4, 31));
-                    if (lane == 0) top2_push(s_red[warp][r], d2, jc);
-                }
-            }
-        }
+        const int live = min(MX_ROWS, nflag - rg * MX_ROWS);
+        if (live <= 2) rescan_item<2>(P, p, rg, ch, qa, qb, n2, nflag, s_red[warp]);
+        else if (live <= 4) rescan_item<4>(P, p, rg, ch, qa, qb, n2, nflag, s_red[warp]);
+        else rescan_item<8>(P, p, rg, ch, qa, qb, n2, nflag, s_red[warp]);
         __syncthreads();
         if (t < MX_ROWS) {
             Top2 v = s_red[0][t];
@@ -721,9 +752,14 @@ __global__ void __launch_bounds__(1024) k_match_sort(const __grid_constant__ Mat
     while (N2 < n) N2 <<= 1;
     const unsigned long long* keys = P.mkeys + (size_t)p * P.nmax;
     for (int i = threadIdx.x; i < N2; i += blockDim.x) s_k[i] = (i < n) ? keys[i] : ~0ull;
-    __syncthreads();
+    // Compare-exchange i of a stage with distance jj <= 32 touches only elements of the 64-aligned block
+    // i / 32, i.e. of the warp's own blocks: those stages need a warp barrier, not a CTA barrier (51 of
+    // the 66 stages at 2048 keys).
+    int prev_jj = 64;
     for (int k = 2; k <= N2; k <<= 1) {
         for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            if (jj > 32 || prev_jj > 32) __syncthreads(); else __syncwarp();
+            prev_jj = jj;
             for (int i = threadIdx.x; i < (N2 >> 1); i += blockDim.x) {
                 const int lo = ((i & ~(jj - 1)) << 1) | (i & (jj - 1));
                 const int hi = lo | jj;
@@ -731,9 +767,9 @@ __global__ void __launch_bounds__(1024) k_match_sort(const __grid_constant__ Mat
                 const bool up = (lo & k) == 0;
                 if ((x > y) == up) { s_k[lo] = y; s_k[hi] = x; }
             }
-            __syncthreads();
         }
     }
+    __syncthreads();
     const int lim = n < P.cap ? n : P.cap;
     for (int r = threadIdx.x; r < lim; r += blockDim.x) {
         const unsigned long long key = s_k[r];
@@ -874,7 +910,7 @@ static int run_match_chunk(SfmCtx* ctx, cudaStream_t s, MatchPlan P, int p0, int
     } else {
         SFM_LAUNCH(ctx, s, "k_flag_all", k_flag_all<<<rowgrid, 256, 0, s>>>(P));
     }
-    SFM_LAUNCH(ctx, s, "k_work_scan", k_work_scan<<<1, 32, 0, s>>>(P));
+    SFM_LAUNCH(ctx, s, "k_work_scan", k_work_scan<<<1, 256, 0, s>>>(P));
     // persistent grids: exactly the CTAs that are resident at once (a second wave would start on items
     // the first one has already walked past)
     int per_sm = 1;
