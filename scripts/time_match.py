@@ -14,12 +14,15 @@ from sfmfromscratch_b200.matcher import match_batch_device
 from sfmfromscratch_b200.synth import synth_descriptor_base, synth_descriptors
 
 
-def leg(n_sets, n, pairs, steps=20):
+def leg(n_sets, n, pairs, steps=20, real=None):
     dev = torch.device("cuda:0")
-    base = synth_descriptor_base(n)
-    sets = np.stack([synth_descriptors(n, i, base=base) for i in range(n_sets)])
-    d_sets = torch.from_numpy(sets).to(dev)
-    d_cnt = torch.full((n_sets,), n, dtype=torch.int32, device=dev)
+    if real is None:
+        base = synth_descriptor_base(n)
+        sets = np.stack([synth_descriptors(n, i, base=base) for i in range(n_sets)])
+        d_sets = torch.from_numpy(sets).to(dev)
+        d_cnt = torch.full((n_sets,), n, dtype=torch.int32, device=dev)
+    else:
+        d_sets, d_cnt = real
     d_pairs = torch.from_numpy(pairs).to(dev)
     for _ in range(3):
         match_batch_device(d_sets, d_cnt, d_pairs, 0.8, cap=n)
@@ -49,11 +52,29 @@ def leg(n_sets, n, pairs, steps=20):
     sub = d_pairs[:2].contiguous()
     r1 = match_batch_device(d_sets, d_cnt, sub, 0.8, cap=n)
     r2 = match_batch_device(d_sets, d_cnt, sub, 0.8, cap=n, mode=N.SFM_MATCH_EXACT)
-    same = all(torch.equal(x, y) for x, y in zip(r1[:3], r2[:3]))
+    same = torch.equal(r1[2], r2[2])
+    for q in range(sub.shape[0]):
+        k = int(r1[2][q])
+        same = same and torch.equal(r1[0][q, :k], r2[0][q, :k]) and torch.equal(r1[1][q, :k], r2[1][q, :k])
     print("    auto == exact on 2 pairs:", same)
     assert same
+    per = mst.cpu().numpy()
+    print("    per pair flagged rows (first 8):", per[:8, 0].tolist(), " groups:", per[:8, 1].tolist(), " counts:", d_cnt[:8].tolist())
+
+
+def real_sets(n_img=32, distinct=8):
+    """The bench step's descriptors: ScaleRotInvSIFT defaults on synthetic 1080p images."""
+    from sfmfromscratch_b200.extractor import extract_batch_device, make_params
+    from sfmfromscratch_b200.synth import synth_image
+    imgs = np.stack([synth_image(1080, 1920, s) for s in range(distinct)])
+    imgs = torch.from_numpy(np.concatenate([imgs] * (n_img // distinct))).cuda()
+    params, keep = make_params({}, pyramid=True)
+    out = extract_batch_device(imgs, params, want_aux=False)
+    return out['desc'].contiguous(), out['count'].contiguous()
 
 
 if __name__ == "__main__":
+    d, c = real_sets()
+    leg(32, d.shape[1], np.stack([np.arange(31), np.arange(1, 32)], 1).astype(np.int32), real=(d, c))
     leg(12, 8192, PL.all_pairs(12))
     leg(32, 1700, np.stack([np.arange(31), np.arange(1, 32)], 1).astype(np.int32))

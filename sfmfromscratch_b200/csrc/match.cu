@@ -129,7 +129,7 @@ __device__ __forceinline__ void top2_push(Top2& s, float d, int j) {
 // Cauchy-Schwarz on the residual norms, accumulation, index packing, and the
 // float32 rounding of the exact sum itself).  Uncertified rows go to the exact
 // scan.  NV = candidate entries per lane (ceil(n_lists * 4 / 8)).
-constexpr int RC_ROWS = 256;           // rows per CTA: phase 1 is thread per row
+constexpr int RC_ROWS = 256;           // most rows per CTA (phase 1 is thread per row); small batches use fewer, for more CTAs
 constexpr int RC_TEAMS = 32;           // phase 2: 8-lane teams over the surviving rows
 constexpr int RC_SQ_STRIDE = SFM_DESC_DIM + 8;   // staging row of squares: 544 bytes keeps the 4 columns on distinct banks
 
@@ -142,7 +142,7 @@ constexpr int RC_SQ_STRIDE = SFM_DESC_DIM + 8;   // staging row of squares: 544 
 // with full teams.
 // Phase 2 (8 lanes per row): as described above.
 template <int NV>
-__global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant__ MatchPlan P) {
+__global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant__ MatchPlan P, int rows_per_cta) {
     extern __shared__ __align__(16) unsigned char rc_smem[];
     float (*s_sq)[MT_SUB][RC_SQ_STRIDE] = reinterpret_cast<float (*)[MT_SUB][RC_SQ_STRIDE]>(rc_smem);
     __shared__ double s_ebase[RC_ROWS], s_na[RC_ROWS];
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
     if (threadIdx.x == 0) { s_n = 0; s_visited = 0; }
     __syncthreads();
     {
-        const int row = blockIdx.x * RC_ROWS + threadIdx.x;
-        if (row < n1) {
+        const int row = blockIdx.x * rows_per_cta + threadIdx.x;
+        if (row < n1 && (int)threadIdx.x < rows_per_cta) {
             const uint4* l4 = reinterpret_cast<const uint4*>(P.cands + ((size_t)p * P.nmax_pad + row) * (size_t)E);
             float k0 = INFINITY, k1 = INFINITY;
             for (int e = 0; e < E / 4; ++e) {
@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
     const float* B = P.set_ptr[qb];
     int visited = 0;
     for (int slot = team; slot < n_live; slot += RC_TEAMS) {
-        const int row = blockIdx.x * RC_ROWS + (int)s_rows[slot];
+        const int row = blockIdx.x * rows_per_cta + (int)s_rows[slot];
         const double e_base = s_ebase[slot], na = s_na[slot];
         float4 a4[4];                                      // elements 32 i + 4 j .. + 3 of the query row
         {
@@ -354,9 +354,22 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
         const bool certified =
             (Lmin == INFINITY) ||
             ((double)Lmin + na - (e_base + q_rel * fabs((double)Lmin)) > (double)best.d1);
+        // An uncertified row whose ratio test is decided anyway needs no rescan.  Unseen columns are at
+        // least lb = Lmin + |a|^2 - E away, so the true nearest is >= min(d0, lb) and the true
+        // second-nearest <= d1: when even that ratio exceeds the threshold, or when two columns at
+        // distance exactly 0 were found (d1 = 0 fails the reference's `> 0`), the row emits nothing.
+        bool rejected = false;
+        if (!certified && P.thr >= 0.0f && !P.no_prune) {
+            const double lb = fmax((double)Lmin + na - (e_base + q_rel * fabs((double)Lmin)), 0.0);
+            const double lo0 = fmin((double)best.d0, lb);
+            rejected = best.d1 == 0.0f ||
+                       (best.d1 < INFINITY && lo0 > 0.0 && lo0 * (1.0 - 4e-6) > (double)P.thr * (double)P.thr * (double)best.d1);
+        }
         if (j == 0) {
             const size_t o = (size_t)p * P.nmax + row;
-            if (certified) {
+            if (rejected) {
+                P.res_idx[o] = -1; P.res_d0[o] = 0.f; P.res_d1[o] = 0.f;
+            } else if (certified) {
                 P.res_idx[o] = best.i0; P.res_d0[o] = best.d0; P.res_d1[o] = best.d1;
             } else {
                 const int pos = atomicAdd(&P.flag_cnt[p], 1);
@@ -373,13 +386,17 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
 }
 
 static int launch_match_recheck(SfmCtx* ctx, cudaStream_t s, const MatchPlan& P) {
-    const dim3 grid(ceil_div(P.nmax, RC_ROWS), P.pn);
+    // rows per CTA: 256 when that still gives a few waves of CTAs, fewer for small batches (the kernel is
+    // a chain of dependent gathers per row: with one wave the slowest CTA sets the time)
+    int rows = RC_ROWS;
+    while (rows > 32 && (long long)ceil_div(P.nmax, rows) * P.pn < 8LL * ctx->sm_count) rows >>= 1;
+    const dim3 grid(ceil_div(P.nmax, rows), P.pn);
     const int nv = ceil_div(P.n_lists * MT_TOPK, 8);
     constexpr int smem = RC_TEAMS * MT_SUB * RC_SQ_STRIDE * (int)sizeof(float);
 #define RC_GO(NV)                                                                                          \
     do {                                                                                                   \
         SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_recheck<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        SFM_LAUNCH(ctx, s, "k_match_recheck", k_match_recheck<NV><<<grid, 256, smem, s>>>(P));             \
+        SFM_LAUNCH(ctx, s, "k_match_recheck", k_match_recheck<NV><<<grid, 256, smem, s>>>(P, rows));       \
     } while (0)
     if (nv <= 1) RC_GO(1);
     else if (nv <= 2) RC_GO(2);
