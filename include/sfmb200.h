@@ -189,12 +189,23 @@ typedef enum SfmMatchMode {
     SFM_MATCH_AUTO = 0,     /* tcgen05 fp16 candidate pass + exact float32
                                re-check (+ exact scan of rows whose error bound
                                cannot certify the candidates) */
-    SFM_MATCH_EXACT = 1     /* exact float32 scan of every row (validation) */
+    SFM_MATCH_EXACT = 1,    /* exact float32 scan of every row (validation) */
+    SFM_MATCH_PREPARED = 16 /* flag, OR-ed into the mode of sfm_match_ratio_batch: the
+                               workspace already holds the per-set preparation (fp16
+                               copy, norms) of an earlier call with the same desc_dev,
+                               counts_dev, n_sets and nmax -- only the pair list is new.
+                               All-pairs matching in chunks (configs[4]) prepares the
+                               512 sets once instead of once per chunk. */
 } SfmMatchMode;
 
 /* Workspace bytes for matching n_sets descriptor sets of at most nmax rows over
  * n_pairs pairs. */
 SFM_EXPORT size_t sfm_match_workspace_bytes(int n_sets, int nmax, int n_pairs);
+
+/* Leading bytes of the workspace that hold the per-set preparation: they depend on
+ * (n_sets, nmax) only, so one workspace sized for the largest pair chunk serves every
+ * later SFM_MATCH_PREPARED call over the same sets. */
+SFM_EXPORT size_t sfm_match_prepared_bytes(int n_sets, int nmax);
 
 /*
  * One pair.  f1_dev [n1][128], f2_dev [n2][128] float32 row-major, n2 >= 2.

@@ -18,7 +18,7 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from sfmfromscratch_b200 import pipeline as PL  # noqa: E402
-from sfmfromscratch_b200.matcher import match_batch_device  # noqa: E402
+from sfmfromscratch_b200.matcher import match_batch_device, match_workspace  # noqa: E402
 
 
 def synth_block(n_img, n, seed, dev):
@@ -54,6 +54,13 @@ def main():
     mine = torch.zeros((per, a.n, 128), device=dev)
     mine[: s1 - s0] = synth_block(s1 - s0, a.n, 77 + rank, dev)
     counts = torch.zeros((per,), dtype=torch.int32, device=dev); counts[: s1 - s0] = a.n
+    # one untimed chunk: kernel modules, the tensor-map entry point and the allocator's blocks are in place
+    # before the clock starts (the timed region below still includes the all-gather and every pair)
+    warm_pairs = torch.from_numpy(np.ascontiguousarray(PL.all_pairs(min(per, 24))[: a.chunk])).to(dev)
+    if len(warm_pairs):
+        wws = match_workspace(per, a.n, a.chunk, dev)
+        match_batch_device(mine, counts.clamp(min=2), warm_pairs, 0.8, cap=a.n, ws=wws)
+        del wws
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -64,9 +71,11 @@ def main():
     e1.record()
     pairs = PL.deal_pairs(PL.all_pairs(a.images), rank, world)
     total = torch.zeros((), dtype=torch.int64, device=dev)
+    ws = match_workspace(desc_all.shape[0], a.n, a.chunk, dev)       # the sets are prepared by the first chunk only
+    pairs_dev = torch.from_numpy(np.ascontiguousarray(pairs)).to(dev)
     for c0 in range(0, len(pairs), a.chunk):
-        pc = torch.from_numpy(np.ascontiguousarray(pairs[c0:c0 + a.chunk])).to(dev)
-        m, c, cnt = match_batch_device(desc_all, counts_all, pc, 0.8, cap=a.n)
+        pc = pairs_dev[c0:c0 + a.chunk]
+        m, c, cnt = match_batch_device(desc_all, counts_all, pc, 0.8, cap=a.n, ws=ws, prepared=c0 > 0)
         total += cnt.sum()          # stays on the device: no host sync per chunk
     e2.record()
     torch.cuda.synchronize()

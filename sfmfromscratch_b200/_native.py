@@ -20,6 +20,7 @@ SFM_ERR_CAPACITY = -4
 SFM_ERR_UNSUPPORTED = -5
 SFM_MATCH_AUTO = 0
 SFM_MATCH_EXACT = 1
+SFM_MATCH_PREPARED = 16
 DESC_DIM = 128
 
 # every symbol include/sfmb200.h declares
@@ -29,7 +30,7 @@ EXPORTS = [
     "sfm_extract_default_params", "sfm_extract_max_keypoints", "sfm_extract_workspace_bytes",
     "sfm_extract_batch", "sfm_extract_status", "sfm_harris_response",
     "sfm_ingest_workspace_bytes", "sfm_ingest_rgb8",
-    "sfm_match_workspace_bytes", "sfm_match_ratio", "sfm_match_ratio_batch",
+    "sfm_match_workspace_bytes", "sfm_match_prepared_bytes", "sfm_match_ratio", "sfm_match_ratio_batch",
     "sfm_matches_to_coords", "sfm_ransac_sample_indices", "sfm_ransac_workspace_bytes", "sfm_find_inliers",
     "sfm_ransac_camera_motion", "sfm_ransac_debug_views",
     "sfm_associate_nearest", "sfm_dedup_workspace_bytes", "sfm_dedup_points",
@@ -100,6 +101,8 @@ def load_library() -> C.CDLL:
         L.sfm_ingest_rgb8.argtypes = [vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, C.c_size_t, fp]
         L.sfm_match_workspace_bytes.argtypes = [C.c_int, C.c_int, C.c_int]
         L.sfm_match_workspace_bytes.restype = C.c_size_t
+        L.sfm_match_prepared_bytes.argtypes = [C.c_int, C.c_int]
+        L.sfm_match_prepared_bytes.restype = C.c_size_t
         L.sfm_match_ratio.argtypes = [vp, vp, fp, C.c_int, fp, C.c_int, C.c_int, C.c_float, C.c_int, vp,
                                       C.c_size_t, i32p, fp, i32p, C.c_int]
         L.sfm_match_ratio_batch.argtypes = [vp, vp, fp, i32p, C.c_int, C.c_int, i32p, C.c_int, C.c_float,

@@ -389,7 +389,11 @@ static int launch_match_recheck(SfmCtx* ctx, cudaStream_t s, const MatchPlan& P)
     // rows per CTA: 256 when that still gives a few waves of CTAs, fewer for small batches (the kernel is
     // a chain of dependent gathers per row: with one wave the slowest CTA sets the time)
     int rows = RC_ROWS;
-    while (rows > 32 && (long long)ceil_div(P.nmax, rows) * P.pn < 8LL * ctx->sm_count) rows >>= 1;
+    {
+        static const int min_rows = [] { const char* e = getenv("SFM_RC_MIN_ROWS"); return e ? atoi(e) : 32; }();
+        static const int waves = [] { const char* e = getenv("SFM_RC_WAVES"); return e ? atoi(e) : 8; }();
+        while (rows > min_rows && (long long)ceil_div(P.nmax, rows) * P.pn < (long long)waves * ctx->sm_count) rows >>= 1;
+    }
     const dim3 grid(ceil_div(P.nmax, rows), P.pn);
     const int nv = ceil_div(P.n_lists * MT_TOPK, 8);
     constexpr int smem = RC_TEAMS * MT_SUB * RC_SQ_STRIDE * (int)sizeof(float);
@@ -849,10 +853,13 @@ static int choose_splits(int n_pairs, int nmax_pad) {
 }
 
 struct MatchWs {
-    size_t set_ptr, set_cnt, pairs, zero_begin, setmax, flag_cnt, mcount, stats, work_off, zero_end;
-    size_t h16, nb, hatn, resn, cands, res_idx, res_d0, res_d1, flag_rows, part, mkeys, midx, total;
+    size_t set_ptr, set_cnt, setmax, h16, nb, hatn, resn, pair_begin;
+    size_t pairs, zero_begin, flag_cnt, mcount, stats, work_off, zero_end;
+    size_t cands, res_idx, res_d0, res_d1, flag_rows, part, mkeys, midx, total;
 };
 
+// Set-side arrays first: their offsets depend on (n_sets, nmax) only, so a workspace prepared once
+// (k_match_prep) serves any number of later calls with SFM_MATCH_PREPARED and other pair lists.
 static void match_layout(int n_sets, int nmax, int n_pairs, MatchPlan& P, MatchWs& ws) {
     P.n_sets = n_sets; P.nmax = nmax; P.n_pairs = n_pairs;
     P.nmax_pad = (int)align_up((size_t)std::max(nmax, 1), MT_ROWS);
@@ -867,18 +874,19 @@ static void match_layout(int n_sets, int nmax, int n_pairs, MatchPlan& P, MatchW
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
     ws.set_ptr = take(sizeof(void*) * n_sets);
     ws.set_cnt = take(sizeof(int32_t) * n_sets);
+    ws.setmax = take(sizeof(float) * 4 * n_sets);
+    ws.h16 = take(sizeof(__half) * rows * SFM_DESC_DIM);
+    ws.nb = take(sizeof(float) * rows);
+    ws.hatn = take(sizeof(float) * rows);
+    ws.resn = take(sizeof(float) * rows);
+    ws.pair_begin = o;
     ws.pairs = take(sizeof(int32_t) * 2 * n_pairs);
     ws.zero_begin = o;
-    ws.setmax = take(sizeof(float) * 4 * n_sets);
     ws.flag_cnt = take(sizeof(int32_t) * n_pairs);
     ws.mcount = take(sizeof(int32_t) * n_pairs);
     ws.stats = take(sizeof(int32_t) * 2 * n_pairs);
     ws.work_off = take(sizeof(int32_t) * (n_pairs + 1 + MT_MAX_CHUNKS));
     ws.zero_end = o;
-    ws.h16 = take(sizeof(__half) * rows * SFM_DESC_DIM);
-    ws.nb = take(sizeof(float) * rows);
-    ws.hatn = take(sizeof(float) * rows);
-    ws.resn = take(sizeof(float) * rows);
     ws.cands = take(sizeof(uint32_t) * (size_t)n_pairs * P.nmax_pad * P.n_lists * MT_TOPK);
     ws.res_idx = take(sizeof(int32_t) * pr);
     ws.res_d0 = take(sizeof(float) * pr);
@@ -954,17 +962,19 @@ static int run_match_chunk(SfmCtx* ctx, cudaStream_t s, MatchPlan P, int p0, int
 }
 
 static int run_match(SfmCtx* ctx, cudaStream_t st, MatchPlan& P, const MatchWs& ws, void* workspace,
-                     int32_t* match_out, float* conf_out, int32_t* count_out, int32_t* stats_out) {
+                     int32_t* match_out, float* conf_out, int32_t* count_out, int32_t* stats_out, bool prepared) {
     SFM_CUDA_CHECK(ctx, cudaSetDevice(ctx->device));
     SFM_CUDA_CHECK(ctx, cudaMemsetAsync((char*)workspace + ws.zero_begin, 0, ws.zero_end - ws.zero_begin, st));
+    if (!prepared) SFM_CUDA_CHECK(ctx, cudaMemsetAsync((char*)workspace + ws.setmax, 0, sizeof(float) * 4 * P.n_sets, st));
     const int nt = std::max(P.n_sets, P.n_pairs);
     P.p0 = 0; P.pn = P.n_pairs; P.woff = 0;
+    // (with prepared sets k_match_setup rewrites the same set table and copies this call's pair list)
     SFM_LAUNCH(ctx, st, "k_match_setup", k_match_setup<<<ceil_div(nt, 256), 256, 0, st>>>(P));
-    if (P.mode == SFM_MATCH_AUTO)
+    if (P.mode == SFM_MATCH_AUTO && !prepared)
         SFM_LAUNCH(ctx, st, "k_match_prep", k_match_prep<<<dim3(P.nmax_pad / 8, P.n_sets), 256, 0, st>>>(P));
     // One chunk covering every pair.  (Measured on B200: splitting the batch into pair chunks on two
     // streams so the re-check of one chunk overlaps the tensor-core pass of the next buys nothing --
-    // both are bound by the same L2 -> SM bandwidth: 2.10 ms either way for 66 pairs of 8192 x 8192.)
+    // both are bound by the same L2 -> SM bandwidth.)
     return run_match_chunk(ctx, st, P, 0, P.n_pairs, 0, match_out, conf_out, count_out, stats_out);
 }
 
@@ -983,6 +993,15 @@ size_t sfm_match_workspace_bytes(int n_sets, int nmax, int n_pairs) {
     memset(&P, 0, sizeof(P));
     match_layout(n_sets, nmax, n_pairs, P, ws);
     return ws.total;
+}
+
+size_t sfm_match_prepared_bytes(int n_sets, int nmax) {
+    if (n_sets < 1 || nmax < 1) return 0;
+    MatchPlan P;
+    MatchWs ws;
+    memset(&P, 0, sizeof(P));
+    match_layout(n_sets, nmax, 1, P, ws);
+    return ws.pair_begin;
 }
 
 int sfm_match_ratio(SfmCtx* ctx, void* stream, const float* f1_dev, int n1, const float* f2_dev,
@@ -1008,7 +1027,7 @@ int sfm_match_ratio(SfmCtx* ctx, void* stream, const float* f1_dev, int n1, cons
     match_bind(P, ws, workspace_dev);
     P.f1 = f1_dev; P.f2 = f2_dev; P.n1 = n1; P.n2 = n2;
     P.thr = ratio_threshold; P.mode = mode; P.cap = cap; P.no_prune = match_no_prune();
-    return run_match(ctx, (cudaStream_t)stream, P, ws, workspace_dev, match_out, conf_out, count_out, nullptr);
+    return run_match(ctx, (cudaStream_t)stream, P, ws, workspace_dev, match_out, conf_out, count_out, nullptr, false);
 }
 
 int sfm_match_ratio_batch(SfmCtx* ctx, void* stream, const float* desc_dev, const int32_t* counts_dev,
@@ -1021,6 +1040,8 @@ int sfm_match_ratio_batch(SfmCtx* ctx, void* stream, const float* desc_dev, cons
         return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "NULL pointer");
     if (n_sets < 1 || nmax < 2 || n_pairs < 1) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "bad sizes");
     if ((uintptr_t)desc_dev & 15) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "descriptor pointer must be 16-byte aligned");
+    const bool prepared = (mode & SFM_MATCH_PREPARED) != 0;
+    mode &= ~SFM_MATCH_PREPARED;
     if (mode != SFM_MATCH_AUTO && mode != SFM_MATCH_EXACT) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "bad mode");
     MatchPlan P;
     MatchWs ws;
@@ -1032,7 +1053,7 @@ int sfm_match_ratio_batch(SfmCtx* ctx, void* stream, const float* desc_dev, cons
     match_bind(P, ws, workspace_dev);
     P.desc = desc_dev; P.counts_in = counts_dev; P.pairs_in = pairs_dev;
     P.thr = ratio_threshold; P.mode = mode; P.cap = cap; P.no_prune = match_no_prune();
-    return run_match(ctx, (cudaStream_t)stream, P, ws, workspace_dev, match_out, conf_out, count_out, stats_out);
+    return run_match(ctx, (cudaStream_t)stream, P, ws, workspace_dev, match_out, conf_out, count_out, stats_out, prepared);
 }
 
 }  // extern "C"

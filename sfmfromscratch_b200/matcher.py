@@ -38,10 +38,13 @@ def match_device(f1: torch.Tensor, f2: torch.Tensor, ratio_threshold: float, mod
 
 
 def match_batch_device(desc: torch.Tensor, counts: torch.Tensor, pairs: torch.Tensor, ratio_threshold: float,
-                       mode: int = N.SFM_MATCH_AUTO, cap: Optional[int] = None, want_stats: bool = False):
+                       mode: int = N.SFM_MATCH_AUTO, cap: Optional[int] = None, want_stats: bool = False,
+                       ws: Optional[torch.Tensor] = None, prepared: bool = False):
     """sfm_match_ratio_batch.  desc [n_sets,nmax,128] f32, counts [n_sets] i32,
     pairs [n_pairs,2] i32, all CUDA.  Returns (matches [P,cap,2], conf [P,cap],
-    count [P][, stats [P,2]])."""
+    count [P][, stats [P,2]]).  `ws` is a caller-kept workspace (uint8, at least
+    sfm_match_workspace_bytes); with `prepared` it already holds the per-set
+    preparation of an earlier call over the same desc / counts (SFM_MATCH_PREPARED)."""
     if not (desc.is_cuda and counts.is_cuda and pairs.is_cuda):
         raise ValueError("desc, counts and pairs must be CUDA tensors")
     if desc.dtype != torch.float32 or desc.dim() != 3 or desc.shape[2] != N.DESC_DIM:
@@ -56,17 +59,29 @@ def match_batch_device(desc: torch.Tensor, counts: torch.Tensor, pairs: torch.Te
     ctx = N.get_ctx(desc.device.index)
     with torch.cuda.device(desc.device):
         nbytes = L.sfm_match_workspace_bytes(n_sets, nmax, P)
-        ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=desc.device)
+        if ws is None:
+            if prepared:
+                raise ValueError("prepared=True needs the workspace of the preparing call")
+            ws = torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=desc.device)
+        elif ws.numel() < nbytes or ws.dtype != torch.uint8 or not ws.is_cuda:
+            raise ValueError(f"workspace too small: {ws.numel()} < {nbytes}")
         m = torch.empty((P, cap, 2), dtype=torch.int32, device=desc.device)
         c = torch.empty((P, cap), dtype=torch.float32, device=desc.device)
         cnt = torch.zeros((P,), dtype=torch.int32, device=desc.device)
         st = torch.zeros((P, 2), dtype=torch.int32, device=desc.device) if want_stats else None
         N.check(L.sfm_match_ratio_batch(ctx, _stream_ptr(), desc.data_ptr(), counts.data_ptr(), n_sets, nmax,
-                                        pairs.data_ptr(), P, float(np.float32(ratio_threshold)), mode,
-                                        ws.data_ptr(), nbytes, m.data_ptr(), c.data_ptr(), cnt.data_ptr(),
+                                        pairs.data_ptr(), P, float(np.float32(ratio_threshold)),
+                                        mode | (N.SFM_MATCH_PREPARED if prepared else 0),
+                                        ws.data_ptr(), ws.numel(), m.data_ptr(), c.data_ptr(), cnt.data_ptr(),
                                         st.data_ptr() if want_stats else None, cap), ctx)
         ws.record_stream(torch.cuda.current_stream())
     return (m, c, cnt, st) if want_stats else (m, c, cnt)
+
+
+def match_workspace(n_sets: int, nmax: int, n_pairs: int, device) -> torch.Tensor:
+    """A workspace for match_batch_device(ws=...) over up to n_pairs pairs per call."""
+    nbytes = N.load_library().sfm_match_workspace_bytes(n_sets, nmax, n_pairs)
+    return torch.empty((max(nbytes, 1),), dtype=torch.uint8, device=device)
 
 
 class NNRatioFeatureMatcher:

@@ -162,3 +162,31 @@ def test_4k_pair_20k_descriptors_auto_equals_exact():
     mg = res[0][0][sel].copy()
     mg[:, 0] = np.searchsorted(rows, mg[:, 0])
     assert_matches_identical(mg, res[0][1][sel], mo, co)
+
+
+def test_prepared_workspace_reused_across_pair_chunks():
+    """SFM_MATCH_PREPARED: the per-set preparation of the first chunk serves later chunks with
+    other pair lists (and other pair counts) in the same workspace; results equal one-shot calls."""
+    import torch
+    _, S = _mods()
+    from sfmfromscratch_b200.matcher import match_workspace
+    from sfmfromscratch_b200.synth import synth_descriptor_base, synth_descriptors
+    base = synth_descriptor_base(1200)
+    sizes = (1200, 1100, 900, 1000, 1200)
+    desc = torch.zeros((len(sizes), 1200, 128), dtype=torch.float32, device='cuda')
+    for i, n in enumerate(sizes):
+        desc[i, :n] = torch.from_numpy(synth_descriptors(n, 40 + i, base=base)).cuda()
+    counts = torch.tensor(sizes, dtype=torch.int32, device='cuda')
+    chunks = [[(0, 1), (1, 2), (2, 3)], [(3, 4), (4, 0)], [(2, 0), (1, 4), (3, 1), (0, 4)]]
+    ws = match_workspace(len(sizes), 1200, 4, 'cuda')
+    for k, ch in enumerate(chunks):
+        pairs = torch.tensor(ch, dtype=torch.int32, device='cuda')
+        got = S.match_batch_device(desc, counts, pairs, 0.8, ws=ws, prepared=k > 0)
+        ref = S.match_batch_device(desc, counts, pairs, 0.8)
+        assert torch.equal(got[2], ref[2])
+        for q in range(len(ch)):
+            n = int(ref[2][q])
+            assert n > 50
+            assert torch.equal(got[0][q, :n], ref[0][q, :n]) and torch.equal(got[1][q, :n], ref[1][q, :n])
+    with pytest.raises(ValueError):
+        S.match_batch_device(desc, counts, pairs, 0.8, prepared=True)
