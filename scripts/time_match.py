@@ -74,7 +74,15 @@ def real_sets(n_img=32, distinct=8):
 
 
 if __name__ == "__main__":
-    d, c = real_sets()
-    leg(32, d.shape[1], np.stack([np.arange(31), np.arange(1, 32)], 1).astype(np.int32), real=(d, c))
-    leg(12, 8192, PL.all_pairs(12))
-    leg(32, 1700, np.stack([np.arange(31), np.arange(1, 32)], 1).astype(np.int32))
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--leg", default="all", choices=["all", "big", "real"])
+    ap.add_argument("--steps", type=int, default=20)
+    a = ap.parse_args()
+    if a.leg in ("all", "real"):
+        d, c = real_sets()
+        leg(32, d.shape[1], np.stack([np.arange(31), np.arange(1, 32)], 1).astype(np.int32), steps=a.steps, real=(d, c))
+    if a.leg in ("all", "big"):
+        leg(12, 8192, PL.all_pairs(12), steps=a.steps)
+    if a.leg == "all":
+        leg(32, 1700, np.stack([np.arange(31), np.arange(1, 32)], 1).astype(np.int32), steps=a.steps)
