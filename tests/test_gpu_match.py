@@ -190,3 +190,36 @@ def test_prepared_workspace_reused_across_pair_chunks():
             assert torch.equal(got[0][q, :n], ref[0][q, :n]) and torch.equal(got[1][q, :n], ref[1][q, :n])
     with pytest.raises(ValueError):
         S.match_batch_device(desc, counts, pairs, 0.8, prepared=True)
+
+
+@pytest.mark.parametrize("thr", [0.0, 0.3, 0.64, 0.8, 0.95, 1.0, 1.25, -0.5])
+def test_ratio_prune_is_exact_across_thresholds(thr):
+    """The re-check proves rows rejected from the approximate keys alone (ratio prune) -- the emitted
+    set must still be the exact scan's for every threshold, including rows whose ratio sits on it.
+    Query rows are train rows plus noise of continuously growing strength, so ratios cover (0, 1];
+    exact duplicates and zero rows are mixed in (d0 = d1 = 0, d1 > 0 with d0 = 0)."""
+    import torch
+    _, S = _mods()
+    rng = np.random.default_rng(7)
+    n1, n2 = 3000, 2777
+    f2 = rng.gamma(0.5, size=(n2, 128)).astype(np.float32)
+    f2 /= np.linalg.norm(f2, axis=1, keepdims=True)
+    f2 = np.sqrt(f2)
+    f2[100:110] = f2[100]                         # ten identical train rows
+    f2[200] = 0.0
+    src = rng.integers(0, n2, size=n1)
+    strength = np.linspace(0.0, 1.5, n1, dtype=np.float32)[:, None]
+    f1 = f2[src] + strength * rng.gamma(0.5, size=(n1, 128)).astype(np.float32) * 0.2
+    f1[5] = f2[100]                               # nearest and second-nearest both at distance 0
+    f1[6] = 0.0                                   # exact hit on the zero row, d1 > 0
+    d1, d2 = torch.from_numpy(f1).cuda(), torch.from_numpy(f2).cuda()
+    res = []
+    for mode in (AUTO, EXACT):
+        m, c, cnt = S.match_device(d1, d2, thr, mode)
+        k = int(cnt.cpu()[0])
+        res.append((m[:k].cpu().numpy(), c[:k].cpu().numpy()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    if thr >= 0.3:
+        assert len(res[0][0]) > 100
+    if thr < 0.0:
+        assert len(res[0][0]) == 0
