@@ -111,6 +111,14 @@ __device__ __forceinline__ void top2_push(Top2& s, float d, int j) {
     else if (d < s.d1) { s.d1 = d; }
 }
 
+// The same for columns that arrive in no particular order (the re-check visits groups by approximate
+// key): among columns at exactly the nearest distance the lowest index wins, as in the ordered scans.
+// Only observable with ratio_threshold >= 1, where tied rows (ratio == 1) are emitted.
+__device__ __forceinline__ void top2_push_any_order(Top2& s, float d, int j) {
+    if (d < s.d0 || (d == s.d0 && j < s.i0)) { s.d1 = s.d0; s.d0 = d; s.i0 = j; }
+    else if (d < s.d1) { s.d1 = d; }
+}
+
 // ------------------------------------------------------------------ re-check of tensor-core candidates
 
 // Eight lanes per query row, four rows per warp.  Entries of the row's
@@ -307,7 +315,7 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
 #pragma unroll
             for (int tm = 0; tm < MT_SUB; ++tm) {
                 const float dd = __shfl_sync(tmask, d2, tm, 8);
-                if (col0 + tm < n2) top2_push(best, dd, col0 + tm);
+                if (col0 + tm < n2) top2_push_any_order(best, dd, col0 + tm);
             }
         };
         // NG candidate groups, MT_SUB columns at a time; the next sub-group's loads are issued once the
