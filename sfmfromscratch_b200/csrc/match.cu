@@ -986,10 +986,11 @@ static int run_match(SfmCtx* ctx, cudaStream_t st, MatchPlan& P, const MatchWs& 
     return run_match_chunk(ctx, st, P, 0, P.n_pairs, 0, match_out, conf_out, count_out, stats_out);
 }
 
-// development knob: SFM_MATCH_NO_PRUNE=1 re-checks every row (measures what the ratio prune saves)
+// development knob: SFM_MATCH_NO_PRUNE=1 re-checks every row (measures what the ratio prune saves; read
+// at every call so a script can compare the two settings in one process)
 static int match_no_prune() {
-    static const int v = [] { const char* e = getenv("SFM_MATCH_NO_PRUNE"); return (e && e[0] == '1') ? 1 : 0; }();
-    return v;
+    const char* e = getenv("SFM_MATCH_NO_PRUNE");
+    return (e && e[0] == '1') ? 1 : 0;
 }
 
 extern "C" {
