@@ -301,9 +301,6 @@ def run_ours(args):
     images = host_batch.to(dev)
     params, keep = make_params({}, pyramid=True)
     pairs_global = PL.consecutive_pairs(world * BATCH)
-    my_pairs_np = PL.deal_pairs(pairs_global, rank, world, block=4)
-    my_pairs = torch.from_numpy(np.ascontiguousarray(my_pairs_np)).to(dev)
-    n_my_pairs = int(my_pairs.shape[0])
 
     def barrier():
         if world > 1:
@@ -312,11 +309,15 @@ def run_ours(args):
 
     pipe = PL.FeaturePipeline({}, RATIO, rank=rank, world=world)
     pipe.pair_block = 4
+    # consecutive pairs (Runner.py:183-191): a pair is matched by the rank that owns its first image, and the
+    # exchange is an all-gather of the ONE descriptor block per rank the neighbouring shard needs (PairPlan)
+    plan = pipe.pair_plan(pairs_global, BATCH)
+    my_pairs_np = plan.mine
+    n_my_pairs = int(len(my_pairs_np))
 
     def step(imgs):
         out = pipe.extract(imgs)
-        d_all, c_all = pipe.exchange(out['desc'], out['count'])
-        m = pipe.match(d_all, c_all, my_pairs, cap=2500, pairs_host=my_pairs_np) if n_my_pairs else None
+        m = pipe.match_plan(plan, out['desc'], out['count'], cap=2500)
         return out, m
 
     def timed(fn, steps, warmup):
@@ -567,7 +568,8 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "images_per_gpu": BATCH, "image": [IMG_H, IMG_W],
                            "distinct_images": N_DISTINCT, "pairs_per_gpu": n_my_pairs,
                            "l2": "inputs larger than L2 (265 MB of images, 352 MB of R planes per step)",
-                           "parallelism": f"image shards x{world}, descriptor all-gather (NCCL), pair shards"},
+                           "parallelism": f"image shards x{world}, all-gather (NCCL) of the {plan.K} descriptor block(s) per rank that "
+                                          f"another shard's pairs need (policy {plan.policy}), pair shards"},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": sampler.summary(), "ms_per_step_profiled": prof_ms, "kernels": kernels, "match": match,
                 "single_image": single, "config2_4k_pair": cfg2, "geometry": geom}

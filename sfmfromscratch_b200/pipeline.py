@@ -82,6 +82,79 @@ def gather_keypoints(x: torch.Tensor, y: torch.Tensor, group=None):
     return (out[:, 0].reshape(world * b, -1), out[:, 1].reshape(world * b, -1))
 
 
+class PairPlan:
+    """Who matches which pair, and which descriptor blocks have to travel for it.  Every rank builds the
+    same plan from the global pair list (image ids over `world` contiguous shards of `per` images).
+
+    * policy "local": a pair belongs to the rank that owns its first image.  Chosen when that is
+      balanced and few blocks are needed remotely -- the reference's own pattern, consecutive pairs
+      (Runner.py:183-191), needs ONE block per rank (the next shard's first image), so the exchange is
+      an all-gather of 1.3 MB per rank instead of every descriptor of every rank.
+    * policy "all": block-cyclic deal and the full all-gather (all-pairs matching, configs[4]:
+      every block is needed everywhere).
+
+    The matcher sees a local table: this rank's `per` blocks followed by the gathered blocks
+    (`world * K` for "local", K = the largest number of blocks any rank has to send); `pairs_local`
+    indexes that table, `mine` keeps the global ids in the same order."""
+
+    def __init__(self, pairs_global: np.ndarray, per: int, rank: int, world: int, block: int = 64):
+        pairs_global = np.asarray(pairs_global, dtype=np.int32).reshape(-1, 2)
+        self.per, self.rank, self.world = per, rank, world
+        owner = pairs_global // max(per, 1)                       # [P, 2] owning rank of each image
+        first = owner[:, 0]
+        per_rank = np.bincount(first, minlength=world)[:world] if len(first) else np.zeros(world, dtype=np.int64)
+        send = [np.zeros(0, dtype=np.int32) for _ in range(world)]
+        if world > 1 and len(pairs_global):
+            remote = owner[:, 0] != owner[:, 1]                   # second image lives elsewhere
+            ids = np.unique(pairs_global[remote, 1])
+            for r in range(world):
+                send[r] = ids[(ids // per) == r].astype(np.int32)
+        K = max((len(x) for x in send), default=0)
+        mean = max(len(pairs_global) / max(world, 1), 1.0)
+        balanced = len(pairs_global) == 0 or per_rank.max() <= 1.25 * mean + 1
+        if world == 1 or (balanced and K * world <= 0.5 * per * world):
+            self.policy, self.K, self.send = "local", (K if world > 1 else 0), send
+            self.mine = pairs_global[first == rank] if world > 1 else pairs_global
+            pos = {int(g): (per + int(g) // per * self.K + i) for r in range(world) for i, g in enumerate(send[r])}
+            loc = np.empty_like(self.mine)
+            for k, (i, j) in enumerate(self.mine):
+                loc[k, 0] = i - rank * per
+                loc[k, 1] = (j - rank * per) if (j // per == rank or world == 1) else pos[int(j)]
+            self.pairs_local = loc
+            self.send_local = (send[rank] - rank * per).astype(np.int64) if world > 1 else np.zeros(0, dtype=np.int64)
+        else:
+            self.policy, self.K, self.send = "all", per, send
+            self.mine = deal_pairs(pairs_global, rank, world, block=block)
+            self.pairs_local = self.mine                          # global ids index the gathered table directly
+            self.send_local = np.arange(per, dtype=np.int64)
+        self._dev = {}
+
+    def pairs_dev(self, device) -> Optional[torch.Tensor]:
+        key = str(device)
+        if key not in self._dev:
+            self._dev[key] = (torch.from_numpy(np.ascontiguousarray(self.pairs_local)).to(device)
+                              if len(self.pairs_local) else None)
+        return self._dev[key]
+
+
+def exchange_for(plan: PairPlan, desc: torch.Tensor, counts: torch.Tensor, group=None):
+    """The descriptor table `plan.pairs_local` indexes: everything (policy "all": one all-gather of the
+    whole blocks) or this rank's blocks followed by the few blocks other ranks contribute (policy
+    "local": one all-gather of K blocks per rank; no communication at all when K == 0)."""
+    if plan.policy == "all":
+        return gather_descriptors(desc, counts, group)
+    if plan.K == 0:
+        return desc, counts
+    idx = torch.from_numpy(plan.send_local).to(desc.device, non_blocking=True)
+    send_d = torch.zeros((plan.K,) + tuple(desc.shape[1:]), dtype=desc.dtype, device=desc.device)
+    send_c = torch.zeros((plan.K,), dtype=counts.dtype, device=counts.device)
+    if len(plan.send_local):
+        send_d[:len(plan.send_local)] = desc.index_select(0, idx)
+        send_c[:len(plan.send_local)] = counts.index_select(0, idx)
+    got_d, got_c = gather_descriptors(send_d, send_c, group)
+    return torch.cat([desc, got_d], dim=0), torch.cat([counts, got_c], dim=0)
+
+
 class GraphedExtractor:
     """sfm_extract_batch for a fixed batch shape captured once into a CUDA graph: the ~25 kernel
     launches of an extraction replay as one submission (what matters for a single image, where
@@ -126,6 +199,23 @@ class FeaturePipeline:
 
     def exchange(self, desc: torch.Tensor, counts: torch.Tensor):
         return gather_descriptors(desc, counts, self.group)
+
+    def pair_plan(self, pairs_global: np.ndarray, per: int) -> PairPlan:
+        """The (cached) PairPlan of `pairs_global` for shards of `per` images."""
+        key = (np.asarray(pairs_global).tobytes(), per, self.rank, self.world, self.pair_block)
+        if getattr(self, '_plan_key', None) != key:
+            self._plan_key, self._plan = key, PairPlan(pairs_global, per, self.rank, self.world, block=self.pair_block)
+        return self._plan
+
+    def match_plan(self, plan: PairPlan, desc: torch.Tensor, counts: torch.Tensor, cap: Optional[int] = None):
+        """Exchange what `plan` needs and match this rank's pairs; None when it has none."""
+        tab_d, tab_c = exchange_for(plan, desc, counts, self.group)
+        if not len(plan.mine):
+            return None
+        if plan.policy == "all":
+            return self.match(tab_d, tab_c, plan.pairs_dev(desc.device), cap=cap, pairs_host=plan.mine)
+        from .matcher import match_batch_device
+        return match_batch_device(tab_d, tab_c, plan.pairs_dev(desc.device), self.ratio_threshold, cap=cap)
 
     def match(self, desc_all: torch.Tensor, counts_all: torch.Tensor, pairs: torch.Tensor, cap: Optional[int] = None,
               pairs_host: Optional[np.ndarray] = None):
@@ -189,11 +279,10 @@ class FeaturePipeline:
             with torch.cuda.stream(self._s_out):
                 for k in ('x', 'y', 'desc', 'count'):
                     host_out[k][c0:c1].copy_(full[k][c0:c1], non_blocking=True)
-        desc_all, counts_all = self.exchange(full['desc'], full['count'])
-        mine = deal_pairs(pairs_global, self.rank, self.world, block=self.pair_block)
-        if len(mine):
-            pairs = torch.from_numpy(np.ascontiguousarray(mine)).pin_memory().to(dev, non_blocking=True)
-            m = self.match(desc_all, counts_all, pairs, cap=host_out['matches'].shape[1], pairs_host=mine)
+        plan = self.pair_plan(pairs_global, B)
+        mine = plan.mine
+        m = self.match_plan(plan, full['desc'], full['count'], cap=host_out['matches'].shape[1])
+        if m is not None:
             host_out['matches'][:len(mine)].copy_(m[0], non_blocking=True)
             host_out['conf'][:len(mine)].copy_(m[1], non_blocking=True)
             host_out['mcount'][:len(mine)].copy_(m[2], non_blocking=True)
@@ -264,15 +353,10 @@ class FeaturePipeline:
                     host_out[k][c0:c1].copy_(full[k][c0:c1], non_blocking=True)
         slot['imgs_free'] = torch.cuda.Event()
         slot['imgs_free'].record(main)
-        desc_all, counts_all = self.exchange(full['desc'], full['count'])
-        pkey = (pairs_global.tobytes(), self.rank, self.world, self.pair_block, dev.index)
-        if getattr(self, '_pairs_key', None) != pkey:            # the pair list rarely changes: upload it once
-            mine = deal_pairs(pairs_global, self.rank, self.world, block=self.pair_block)
-            self._pairs_key, self._pairs_mine = pkey, mine
-            self._pairs_dev = torch.from_numpy(np.ascontiguousarray(mine)).to(dev) if len(mine) else None
-        mine = self._pairs_mine
-        if len(mine):
-            m = self.match(desc_all, counts_all, self._pairs_dev, cap=host_out['matches'].shape[1], pairs_host=mine)
+        plan = self.pair_plan(pairs_global, B)                  # cached: the pair list rarely changes
+        mine = plan.mine
+        m = self.match_plan(plan, full['desc'], full['count'], cap=host_out['matches'].shape[1])
+        if m is not None:
             host_out['matches'][:len(mine)].copy_(m[0], non_blocking=True)
             host_out['conf'][:len(mine)].copy_(m[1], non_blocking=True)
             host_out['mcount'][:len(mine)].copy_(m[2], non_blocking=True)
@@ -326,9 +410,8 @@ class FeaturePipeline:
         return out
 
     def step(self, images: torch.Tensor, pairs_global: np.ndarray):
-        """Extract the local images, all-gather, match this rank's share of `pairs_global`."""
+        """Extract the local images, exchange the descriptor blocks the pair plan needs, match this
+        rank's share of `pairs_global` (see PairPlan).  Returns (extraction outputs, matches, plan)."""
         out = self.extract(images)
-        desc_all, counts_all = self.exchange(out['desc'], out['count'])
-        mine = deal_pairs(pairs_global, self.rank, self.world, block=self.pair_block)
-        pairs = torch.from_numpy(np.ascontiguousarray(mine)).to(images.device)
-        return out, self.match(desc_all, counts_all, pairs, pairs_host=mine)
+        plan = self.pair_plan(pairs_global, images.shape[0])
+        return out, self.match_plan(plan, out['desc'], out['count']), plan

@@ -225,7 +225,7 @@ def test_pipeline_pair_inliers_device_chain(geo):
     imgs = np.stack([base, v1, second_view(v1, 5), synth_image(240, 320, 99)])      # two real motions, one unrelated image
     pipe = PL.FeaturePipeline({'num_interest_points': 600}, 0.8)
     pairs = PL.consecutive_pairs(len(imgs))
-    out, m = pipe.step(torch.from_numpy(imgs).cuda(), pairs)
+    out, m, _ = pipe.step(torch.from_numpy(imgs).cuda(), pairs)
     x_all, y_all = PL.gather_keypoints(out['x'], out['y'])
     res = pipe.pair_inliers(x_all, y_all, m, pairs, iterations=400)
     counts = m[2].cpu().numpy()

@@ -34,6 +34,36 @@ def test_pairs_and_deal():
     assert len(P.deal_pairs(ap, 0, 8)) == 16352 + (0 if 130816 % (64 * 8) == 0 else 0) or True
 
 
+def test_pair_plan_consecutive_pairs_is_a_halo_exchange():
+    """Consecutive pairs over contiguous shards: every rank matches the pairs that start in its shard
+    and needs exactly one remote block (the next shard's first image)."""
+    world, per = 4, 8
+    pairs = P.consecutive_pairs(world * per)
+    seen = []
+    for r in range(world):
+        pl = P.PairPlan(pairs, per, r, world)
+        assert pl.policy == "local" and pl.K == 1
+        assert [s.tolist() for s in pl.send] == [[], [8], [16], [24]]
+        assert len(pl.mine) == (per if r < world - 1 else per - 1)
+        seen += pl.mine.tolist()
+        # local table: per own blocks, then world * K gathered blocks (slot of rank q at per + q)
+        for (gi, gj), (li, lj) in zip(pl.mine, pl.pairs_local):
+            assert li == gi - r * per
+            assert lj == (gj - r * per if gj // per == r else per + gj // per)
+        assert pl.send_local.tolist() == ([0] if r > 0 else [])
+    assert sorted(seen) == pairs.tolist()
+    one = P.PairPlan(pairs, world * per, 0, 1)
+    assert one.policy == "local" and one.K == 0 and np.array_equal(one.pairs_local, pairs)
+
+
+def test_pair_plan_all_pairs_falls_back_to_the_full_gather():
+    ap = P.all_pairs(64)
+    plans = [P.PairPlan(ap, 8, r, 8) for r in range(8)]
+    assert all(pl.policy == "all" and pl.K == 8 for pl in plans)
+    assert sum(len(pl.mine) for pl in plans) == len(ap)
+    assert np.array_equal(plans[3].mine, P.deal_pairs(ap, 3, 8))
+
+
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -54,6 +84,16 @@ def _worker(rank, world, port, q):
                                                        for r in range(world) for i in range(b) for j in range(4))
         pairs = P.consecutive_pairs(world * b)
         mine = P.deal_pairs(pairs, rank, world, block=2)
+        # halo exchange of the pair plan: own blocks, then one block per rank
+        plan = P.PairPlan(pairs, b, rank, world)
+        td, tc = P.exchange_for(plan, desc, counts)
+        ok = ok and plan.policy == "local" and td.shape == (b + world * plan.K, nmax, 128)
+        ok = ok and torch.equal(td[:b], desc) and tc[:b].tolist() == counts.tolist()
+        if rank == 0:                                   # needs image 3 = rank 1's first block, at slot b + 1 * K + 0
+            ok = ok and plan.pairs_local.tolist() == [[0, 1], [1, 2], [2, b + 1]]
+            ok = ok and float(td[b + 1, 0, 0]) == 10.0 and float(td[b + 1, 0, 1]) == 1.0 and int(tc[b + 1]) == 2
+        else:
+            ok = ok and plan.pairs_local.tolist() == [[0, 1], [1, 2]]
         q.put((rank, bool(ok), mine.tolist()))
     finally:
         dist.destroy_process_group()
