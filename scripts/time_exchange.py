@@ -36,7 +36,6 @@ def timed(fn, n=100):
     a.record()
     for _ in range(n):
         fn()
-    pipe.join()
     b.record()
     torch.cuda.synchronize()
     t = torch.tensor([a.elapsed_time(b) / n], device=dev)
@@ -46,14 +45,6 @@ def timed(fn, n=100):
 
 
 def full():
-    pipe.step_plan(imgs, plan, cap=2500)
-
-
-def full_overlap():
-    pipe.step_plan(imgs, plan, cap=2500, overlap=True)
-
-
-def full_cat():
     o = pipe.extract(imgs)
     pipe.match_plan(plan, o['desc'], o['count'], cap=2500)
 
@@ -70,8 +61,6 @@ res = {
     "exchange_all": timed(lambda: pipe.exchange(out['desc'], out['count'])),
     "match_plan_table": timed(lambda: match_batch_device(tab[0], tab[1], plan.pairs_dev(dev), 0.8, cap=2500)),
     "step_plan": timed(full),
-    "step_plan_cat": timed(full_cat),
-    "step_plan_overlap": timed(full_overlap),
     "step_allgather": timed(full_allgather),
 }
 if rank == 0:
