@@ -316,7 +316,9 @@ def run_ours(args):
     n_my_pairs = int(len(my_pairs_np))
 
     def step(imgs):
-        out = pipe.extract(imgs)
+        # no host wait inside a step: the candidate-overflow flags accumulate on the device and are read
+        # once after the timed region (pipe.overflow_since_last_check)
+        out = pipe.extract(imgs, deferred_check=True)
         m = pipe.match_plan(plan, out['desc'], out['count'], cap=2500)
         return out, m
 
@@ -343,6 +345,8 @@ def run_ours(args):
     l0 = N.launch_count(local)
     sampler.start()
     total_ms = timed(lambda: step(images), args.steps, 0)
+    if pipe.overflow_since_last_check():
+        raise SystemExit("candidate buffer overflow in the timed region")
     sampler.stop_flag = True
     launches = N.launch_count(local) - l0
     sampler.join(timeout=2)

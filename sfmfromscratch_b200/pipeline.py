@@ -193,9 +193,27 @@ class FeaturePipeline:
         self.rank, self.world, self.group = rank, world, group
         self.pair_block = 64
 
-    def extract(self, images: torch.Tensor):
+    def extract(self, images: torch.Tensor, deferred_check: bool = False):
+        """Extraction of a resident batch.  By default the candidate-overflow flag is read back right
+        away (a host wait per call).  With `deferred_check` the flags accumulate on the device -- nothing
+        waits, the host keeps enqueueing -- and `overflow_since_last_check()` reads them once."""
         from .extractor import extract_batch_device
-        return extract_batch_device(images, self.params, want_aux=False)
+        out = extract_batch_device(images, self.params, want_aux=False, check=not deferred_check)
+        if deferred_check:
+            if getattr(self, '_flag_acc', None) is None or self._flag_acc.device != images.device:
+                self._flag_acc = torch.zeros((1,), dtype=torch.int32, device=images.device)
+            self._flag_acc |= out['_flag'][:1]
+        return out
+
+    def overflow_since_last_check(self) -> bool:
+        """True when some `extract(deferred_check=True)` since the last call hit a plateau image: those
+        batches must be redone with `params.cand_full = 1` (what the immediate check does by itself)."""
+        acc = getattr(self, '_flag_acc', None)
+        if acc is None:
+            return False
+        bad = int(acc.cpu()[0]) != 0
+        acc.zero_()
+        return bad
 
     def exchange(self, desc: torch.Tensor, counts: torch.Tensor):
         return gather_descriptors(desc, counts, self.group)
