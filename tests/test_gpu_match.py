@@ -223,3 +223,43 @@ def test_ratio_prune_is_exact_across_thresholds(thr):
         assert len(res[0][0]) > 100
     if thr < 0.0:
         assert len(res[0][0]) == 0
+
+
+def test_ragged_random_batches_auto_equals_exact():
+    """Edge sizes of the re-check / rescan kernels: tiny and ragged sets (2 .. 700 rows; candidate groups
+    and MMA tiles mostly padding), duplicated and zero rows, several thresholds -- the tensor-core path
+    must equal the exact scan pair by pair, and the oracle on the smallest pairs."""
+    import torch
+    O, S = _mods()
+    rng = np.random.default_rng(11)
+    for trial in range(6):
+        n_sets = int(rng.integers(3, 7))
+        nmax = int(rng.choice([2, 3, 9, 64, 257, 700]))
+        sizes = [int(rng.integers(2, nmax + 1)) for _ in range(n_sets)]
+        sizes[0] = nmax
+        desc = np.zeros((n_sets, nmax, 128), np.float32)
+        pool = np.sqrt(rng.gamma(0.4, size=(nmax, 128)).astype(np.float32))
+        for i, n in enumerate(sizes):
+            d = pool[rng.permutation(nmax)[:n]] + 0.05 * i * np.sqrt(rng.gamma(0.4, size=(n, 128)).astype(np.float32))
+            if n > 4:
+                d[1] = d[0]                       # duplicate rows inside a set
+                d[2] = 0.0
+            desc[i, :n] = d
+        pl = [(a, b) for a in range(n_sets) for b in range(n_sets) if a != b][:10] + [(0, 0)]
+        dd = torch.from_numpy(desc).cuda()
+        cc = torch.tensor(sizes, dtype=torch.int32, device='cuda')
+        pp = torch.tensor(pl, dtype=torch.int32, device='cuda')
+        thr = float(rng.choice([0.5, 0.8, 0.97, 1.0]))
+        ra = S.match_batch_device(dd, cc, pp, thr, mode=AUTO)
+        re = S.match_batch_device(dd, cc, pp, thr, mode=EXACT)
+        assert torch.equal(ra[2], re[2]), (trial, nmax, sizes, thr, ra[2].tolist(), re[2].tolist())
+        for q in range(len(pl)):
+            k = int(ra[2][q])
+            assert torch.equal(ra[0][q, :k], re[0][q, :k]) and torch.equal(ra[1][q, :k], re[1][q, :k]), (trial, q, pl[q])
+        if nmax <= 64 and thr < 1.0:              # ties at thr >= 1 are ordered by numpy's unstable argsort in the oracle
+            for q, (a, b) in enumerate(pl[:4]):
+                mo, co = O.NNRatioFeatureMatcher(thr).match_features_ratio_test(desc[a, :sizes[a]], desc[b, :sizes[b]])
+                k = int(ra[2][q])
+                assert k == len(mo)
+                if k:
+                    assert_matches_identical(ra[0][q, :k].cpu().numpy().astype(np.int64), ra[1][q, :k].cpu().numpy(), mo, co)
