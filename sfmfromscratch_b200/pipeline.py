@@ -136,6 +136,13 @@ class PairPlan:
                               if len(self.pairs_local) else None)
         return self._dev[key]
 
+    def send_idx_dev(self, device) -> torch.Tensor:
+        """Local indices of the blocks this rank contributes, on `device` (uploaded once)."""
+        key = "send:" + str(device)
+        if key not in self._dev:
+            self._dev[key] = torch.from_numpy(self.send_local).to(device)
+        return self._dev[key]
+
 
 def exchange_for(plan: PairPlan, desc: torch.Tensor, counts: torch.Tensor, group=None):
     """The descriptor table `plan.pairs_local` indexes: everything (policy "all": one all-gather of the
@@ -145,7 +152,7 @@ def exchange_for(plan: PairPlan, desc: torch.Tensor, counts: torch.Tensor, group
         return gather_descriptors(desc, counts, group)
     if plan.K == 0:
         return desc, counts
-    idx = torch.from_numpy(plan.send_local).to(desc.device, non_blocking=True)
+    idx = plan.send_idx_dev(desc.device)
     send_d = torch.zeros((plan.K,) + tuple(desc.shape[1:]), dtype=desc.dtype, device=desc.device)
     send_c = torch.zeros((plan.K,), dtype=counts.dtype, device=counts.device)
     if len(plan.send_local):
