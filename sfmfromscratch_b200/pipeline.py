@@ -115,11 +115,20 @@ class PairPlan:
         if world == 1 or (balanced and K * world <= 0.5 * per * world):
             self.policy, self.K, self.send = "local", (K if world > 1 else 0), send
             self.mine = pairs_global[first == rank] if world > 1 else pairs_global
-            pos = {int(g): (per + int(g) // per * self.K + i) for r in range(world) for i, g in enumerate(send[r])}
             loc = np.empty_like(self.mine)
-            for k, (i, j) in enumerate(self.mine):
-                loc[k, 0] = i - rank * per
-                loc[k, 1] = (j - rank * per) if (j // per == rank or world == 1) else pos[int(j)]
+            loc[:, 0] = self.mine[:, 0] - (rank * per if world > 1 else 0)
+            j = self.mine[:, 1].astype(np.int64)
+            if world == 1:
+                loc[:, 1] = j
+            else:
+                own = (j // per) == rank
+                # slot of a remote image: after this rank's `per` blocks, rank q's K gathered blocks start at
+                # per + q * K, in the order of send[q] (sorted ids: position by binary search)
+                sent = np.concatenate(send) if K else np.zeros(0, dtype=np.int32)
+                first_of = np.cumsum([0] + [len(x) for x in send])[:-1]
+                q = np.minimum(j // per, world - 1)
+                within = np.searchsorted(sent, j) - first_of[q] if K else np.zeros_like(j)
+                loc[:, 1] = np.where(own, j - rank * per, per + q * self.K + within)
             self.pairs_local = loc
             self.send_local = (send[rank] - rank * per).astype(np.int64) if world > 1 else np.zeros(0, dtype=np.int64)
         else:

@@ -56,6 +56,30 @@ def test_pair_plan_consecutive_pairs_is_a_halo_exchange():
     assert one.policy == "local" and one.K == 0 and np.array_equal(one.pairs_local, pairs)
 
 
+def test_pair_plan_banded_pairs_remap_matches_brute_force():
+    """Pairs (i, i + d), d = 1..3: several remote blocks per rank; the vectorised remap must place
+    every remote image at per + owner * K + (its position in the owner's send list)."""
+    rng = np.random.default_rng(0)
+    for _ in range(10):
+        world, per = int(rng.integers(2, 6)), int(rng.integers(3, 9))
+        n = world * per
+        pairs = np.array([(i, i + d) for i in range(n) for d in (1, 2, 3) if i + d < n], dtype=np.int32)
+        got = []
+        for r in range(world):
+            pl = P.PairPlan(pairs, per, r, world)
+            if pl.policy != "local":
+                got = None
+                break
+            got += pl.mine.tolist()
+            for (gi, gj), (li, lj) in zip(pl.mine, pl.pairs_local):
+                assert li == gi - r * per
+                o = gj // per
+                want = gj - r * per if o == r else per + o * pl.K + list(pl.send[o]).index(gj)
+                assert lj == want
+        if got is not None:
+            assert sorted(got) == sorted(pairs.tolist())
+
+
 def test_pair_plan_all_pairs_falls_back_to_the_full_gather():
     ap = P.all_pairs(64)
     plans = [P.PairPlan(ap, 8, r, 8) for r in range(8)]
