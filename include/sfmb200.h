@@ -190,12 +190,16 @@ typedef enum SfmMatchMode {
                                re-check (+ exact scan of rows whose error bound
                                cannot certify the candidates) */
     SFM_MATCH_EXACT = 1,    /* exact float32 scan of every row (validation) */
-    SFM_MATCH_PREPARED = 16 /* flag, OR-ed into the mode of sfm_match_ratio_batch: the
+    SFM_MATCH_PREPARED = 16,/* flag, OR-ed into the mode of sfm_match_ratio_batch: the
                                workspace already holds the per-set preparation (fp16
                                copy, norms) of an earlier call with the same desc_dev,
                                counts_dev, n_sets and nmax -- only the pair list is new.
                                All-pairs matching in chunks (configs[4]) prepares the
                                512 sets once instead of once per chunk. */
+    SFM_MATCH_NO_PRUNE = 32 /* flag (sfm_match_ratio_batch, validation): re-check every row
+                               exactly instead of skipping the rows whose ratio test the
+                               approximate keys already decide.  Same results, more work:
+                               scripts/check_config5.py measures what the prune saves. */
 } SfmMatchMode;
 
 /* Workspace bytes for matching n_sets descriptor sets of at most nmax rows over
@@ -224,7 +228,10 @@ SFM_EXPORT int sfm_match_ratio(SfmCtx* ctx, void* stream, const float* f1_dev, i
  * is used as a train set), pairs_dev [n_pairs][2] int32 (query set, train set).  Outputs as above with a leading
  * pair dimension: match_out [n_pairs][cap][2], conf_out [n_pairs][cap],
  * count_out [n_pairs].  stats_out (dev, may be NULL) [n_pairs][2] int32:
- * rows re-scanned exactly, candidate groups re-checked.
+ * rows re-scanned exactly, candidate groups re-checked.  Any n_pairs is accepted
+ * (batches above 65 535 pairs run as consecutive chunks on the stream).  A pair
+ * whose set id lies outside [0, n_sets) is matched as a pair of empty sets:
+ * count_out is 0 for it and nothing is read out of bounds.
  */
 SFM_EXPORT int sfm_match_ratio_batch(SfmCtx* ctx, void* stream, const float* desc_dev,
                           const int32_t* counts_dev, int n_sets, int nmax,

@@ -59,15 +59,14 @@ def main():
     for c0 in range(0, len(pairs), a.chunk):
         pc = pairs[c0:c0 + a.chunk]
         res = []
-        for k, knob in enumerate(("0", "1")):
-            os.environ["SFM_MATCH_NO_PRUNE"] = knob
-            m, c, cnt = match_batch_device(desc, counts, pc, 0.8, cap=a.n, ws=ws, prepared=(c0 > 0 or k > 0))
+        for k, knob in enumerate((0, N.SFM_MATCH_NO_PRUNE)):
+            m, c, cnt = match_batch_device(desc, counts, pc, 0.8, mode=N.SFM_MATCH_AUTO | knob, cap=a.n, ws=ws,
+                                           prepared=(c0 > 0 or k > 0))
             res.append(cnt.clone())
             tot[k] += int(cnt.sum())
         diff = torch.nonzero(res[0] != res[1]).flatten().tolist()
         for q in diff:
             bad.append((c0 + q, int(res[0][q]), int(res[1][q])))
-    os.environ["SFM_MATCH_NO_PRUNE"] = "0"
     print("matches with prune", tot[0], "without", tot[1], "pairs that differ", len(bad))
     for (pi, n_p, n_np) in bad[:40]:
         pc = pairs[pi:pi + 1]

@@ -21,6 +21,7 @@ SFM_ERR_UNSUPPORTED = -5
 SFM_MATCH_AUTO = 0
 SFM_MATCH_EXACT = 1
 SFM_MATCH_PREPARED = 16
+SFM_MATCH_NO_PRUNE = 32
 DESC_DIM = 128
 
 # every symbol include/sfmb200.h declares

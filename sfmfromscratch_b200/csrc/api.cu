@@ -45,7 +45,7 @@ int sfm_ctx_create(int device, SfmCtx** out) {
     cudaDeviceProp prop;
     e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { g_noctx_err = cudaGetErrorString(e); return SFM_ERR_CUDA; }
-    if (prop.major != 10) {
+    if (prop.major != 10 || prop.minor != 0) {       // the library holds sm_100a SASS only (no PTX): sm_103 cannot run it
         g_noctx_err = "libsfmb200 is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) +
                       std::to_string(prop.minor);
         return SFM_ERR_UNSUPPORTED;

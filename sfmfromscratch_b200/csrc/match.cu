@@ -44,9 +44,14 @@ __global__ void k_match_setup(const __grid_constant__ MatchPlan P) {
             P.set_cnt[t] = c < 0 ? 0 : (c > P.nmax ? P.nmax : c);
         }
         if (t < P.n_pairs) {
-            P.pairs[2 * t] = P.pairs_in[2 * t];
-            P.pairs[2 * t + 1] = P.pairs_in[2 * t + 1];
+            // set ids outside [0, n_sets) would index the set tables out of bounds: such a pair is redirected to an
+            // empty set pair (no rows, no matches) and counted so the caller can see it (stats are optional)
+            const int a = P.pairs_in[2 * t], b = P.pairs_in[2 * t + 1];
+            const bool ok = a >= 0 && a < P.n_sets && b >= 0 && b < P.n_sets;
+            P.pairs[2 * t] = ok ? a : P.n_sets;
+            P.pairs[2 * t + 1] = ok ? b : P.n_sets;
         }
+        if (t == 0) { P.set_ptr[P.n_sets] = P.desc; P.set_cnt[P.n_sets] = 0; }    // the empty set bad pair ids point at
     }
 }
 
@@ -398,8 +403,7 @@ static int launch_match_recheck(SfmCtx* ctx, cudaStream_t s, const MatchPlan& P)
     // a chain of dependent gathers per row: with one wave the slowest CTA sets the time)
     int rows = RC_ROWS;
     {
-        static const int min_rows = [] { const char* e = getenv("SFM_RC_MIN_ROWS"); return e ? atoi(e) : 32; }();
-        static const int waves = [] { const char* e = getenv("SFM_RC_WAVES"); return e ? atoi(e) : 8; }();
+        constexpr int min_rows = 32, waves = 8;                 // measured on B200 (scripts/time_match.py)
         while (rows > min_rows && (long long)ceil_div(P.nmax, rows) * P.pn < (long long)waves * ctx->sm_count) rows >>= 1;
     }
     const dim3 grid(ceil_div(P.nmax, rows), P.pn);
@@ -845,7 +849,9 @@ static int choose_splits(int n_pairs, int nmax_pad) {
     const int rowblocks = nmax_pad / MT_ROWS;
     const int min_s = (n_tiles + MT_MAX_TILES - 1) / MT_MAX_TILES;
     const long long base = (long long)n_pairs * rowblocks;
-    const int sms = 148;                                   // B200
+    // B200: 148 SMs.  A constant on purpose -- the split count sizes the workspace, and
+    // sfm_match_workspace_bytes has no context to ask (sfm_ctx_create accepts sm_100 devices only)
+    const int sms = 148;
     if (base >= 4LL * sms) return min_s;
     int best = min_s;
     double best_eff = -1.0;
@@ -880,8 +886,8 @@ static void match_layout(int n_sets, int nmax, int n_pairs, MatchPlan& P, MatchW
     const size_t pr = (size_t)n_pairs * std::max(nmax, 1);
     size_t o = 0;
     auto take = [&](size_t bytes) { size_t at = o; o = align_up(o + bytes, 256); return at; };
-    ws.set_ptr = take(sizeof(void*) * n_sets);
-    ws.set_cnt = take(sizeof(int32_t) * n_sets);
+    ws.set_ptr = take(sizeof(void*) * (n_sets + 1));          // + the empty set that out-of-range pair ids are redirected to
+    ws.set_cnt = take(sizeof(int32_t) * (n_sets + 1));
     ws.setmax = take(sizeof(float) * 4 * n_sets);
     ws.h16 = take(sizeof(__half) * rows * SFM_DESC_DIM);
     ws.nb = take(sizeof(float) * rows);
@@ -893,7 +899,7 @@ static void match_layout(int n_sets, int nmax, int n_pairs, MatchPlan& P, MatchW
     ws.flag_cnt = take(sizeof(int32_t) * n_pairs);
     ws.mcount = take(sizeof(int32_t) * n_pairs);
     ws.stats = take(sizeof(int32_t) * 2 * n_pairs);
-    ws.work_off = take(sizeof(int32_t) * (n_pairs + 1 + MT_MAX_CHUNKS));
+    ws.work_off = take(sizeof(int32_t) * (n_pairs + 1));
     ws.zero_end = o;
     ws.cands = take(sizeof(uint32_t) * (size_t)n_pairs * P.nmax_pad * P.n_lists * MT_TOPK);
     ws.res_idx = take(sizeof(int32_t) * pr);
@@ -931,9 +937,9 @@ static void match_bind(MatchPlan& P, const MatchWs& ws, void* base) {
 }
 
 // Everything after the (global) prep for the pair chunk [p0, p0 + pn) on stream `s`.
-static int run_match_chunk(SfmCtx* ctx, cudaStream_t s, MatchPlan P, int p0, int pn, int chunk_idx,
+static int run_match_chunk(SfmCtx* ctx, cudaStream_t s, MatchPlan P, int p0, int pn,
                            int32_t* match_out, float* conf_out, int32_t* count_out, int32_t* stats_out) {
-    P.p0 = p0; P.pn = pn; P.woff = p0 + chunk_idx;
+    P.p0 = p0; P.pn = pn; P.woff = 0;             // chunks are stream-ordered: the work-prefix table is reused
     const dim3 rowgrid(ceil_div(P.nmax, 256), pn);
     if (P.mode == SFM_MATCH_AUTO) {
         int rc = launch_match_tc(ctx, s, P);
@@ -980,17 +986,15 @@ static int run_match(SfmCtx* ctx, cudaStream_t st, MatchPlan& P, const MatchWs& 
     SFM_LAUNCH(ctx, st, "k_match_setup", k_match_setup<<<ceil_div(nt, 256), 256, 0, st>>>(P));
     if (P.mode == SFM_MATCH_AUTO && !prepared)
         SFM_LAUNCH(ctx, st, "k_match_prep", k_match_prep<<<dim3(P.nmax_pad / 8, P.n_sets), 256, 0, st>>>(P));
-    // One chunk covering every pair.  (Measured on B200: splitting the batch into pair chunks on two
-    // streams so the re-check of one chunk overlaps the tensor-core pass of the next buys nothing --
-    // both are bound by the same L2 -> SM bandwidth.)
-    return run_match_chunk(ctx, st, P, 0, P.n_pairs, 0, match_out, conf_out, count_out, stats_out);
-}
-
-// development knob: SFM_MATCH_NO_PRUNE=1 re-checks every row (measures what the ratio prune saves; read
-// at every call so a script can compare the two settings in one process)
-static int match_no_prune() {
-    const char* e = getenv("SFM_MATCH_NO_PRUNE");
-    return (e && e[0] == '1') ? 1 : 0;
+    // Pair chunks of at most 65 535 (gridDim.y of the per-row kernels), one after the other on the caller's stream;
+    // a batch below that is one chunk.  (Measured on B200: overlapping the re-check of one chunk with the
+    // tensor-core pass of the next on two streams buys nothing -- both are bound by the same L2 -> SM bandwidth.)
+    constexpr int MAX_CHUNK = 65535;
+    for (int p0 = 0; p0 < P.n_pairs; p0 += MAX_CHUNK) {
+        const int rc = run_match_chunk(ctx, st, P, p0, std::min(MAX_CHUNK, P.n_pairs - p0), match_out, conf_out, count_out, stats_out);
+        if (rc) return rc;
+    }
+    return SFM_OK;
 }
 
 extern "C" {
@@ -1035,7 +1039,7 @@ int sfm_match_ratio(SfmCtx* ctx, void* stream, const float* f1_dev, int n1, cons
     if (cap < 1) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "cap < 1");
     match_bind(P, ws, workspace_dev);
     P.f1 = f1_dev; P.f2 = f2_dev; P.n1 = n1; P.n2 = n2;
-    P.thr = ratio_threshold; P.mode = mode; P.cap = cap; P.no_prune = match_no_prune();
+    P.thr = ratio_threshold; P.mode = mode; P.cap = cap; P.no_prune = 0;
     return run_match(ctx, (cudaStream_t)stream, P, ws, workspace_dev, match_out, conf_out, count_out, nullptr, false);
 }
 
@@ -1050,7 +1054,8 @@ int sfm_match_ratio_batch(SfmCtx* ctx, void* stream, const float* desc_dev, cons
     if (n_sets < 1 || nmax < 2 || n_pairs < 1) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "bad sizes");
     if ((uintptr_t)desc_dev & 15) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "descriptor pointer must be 16-byte aligned");
     const bool prepared = (mode & SFM_MATCH_PREPARED) != 0;
-    mode &= ~SFM_MATCH_PREPARED;
+    const int no_prune = (mode & SFM_MATCH_NO_PRUNE) ? 1 : 0;
+    mode &= ~(SFM_MATCH_PREPARED | SFM_MATCH_NO_PRUNE);
     if (mode != SFM_MATCH_AUTO && mode != SFM_MATCH_EXACT) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "bad mode");
     MatchPlan P;
     MatchWs ws;
@@ -1061,7 +1066,7 @@ int sfm_match_ratio_batch(SfmCtx* ctx, void* stream, const float* desc_dev, cons
     if (cap < 1) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "cap < 1");
     match_bind(P, ws, workspace_dev);
     P.desc = desc_dev; P.counts_in = counts_dev; P.pairs_in = pairs_dev;
-    P.thr = ratio_threshold; P.mode = mode; P.cap = cap; P.no_prune = match_no_prune();
+    P.thr = ratio_threshold; P.mode = mode; P.cap = cap; P.no_prune = no_prune;
     return run_match(ctx, (cudaStream_t)stream, P, ws, workspace_dev, match_out, conf_out, count_out, stats_out, prepared);
 }
 

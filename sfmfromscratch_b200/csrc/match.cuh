@@ -19,11 +19,10 @@ constexpr float MT_INVALID = 1.0e29f;    // packed values >= this are empty slot
 constexpr int MX_ROWS = 8;            // flagged rows per exact-scan work item
 constexpr int MX_COLS = 1024;         // columns per exact-scan work item
 constexpr int MT_MAX_SPLITS = 16;
-constexpr int MT_MAX_CHUNKS = 4;       // pair chunks overlapped on two internal streams
 
 struct MatchPlan {
     int n_sets, nmax, nmax_pad, n_pairs;
-    int p0, pn, woff, no_prune;       // pair chunk [p0, p0+pn) this launch covers; its slot in work_off; knob
+    int p0, pn, woff, no_prune;       // pair chunk [p0, p0+pn) this launch covers; offset into work_off; validation flag
     int n_splits, tiles_per_split, n_tiles, n_lists;
     int n_xchunks;                    // exact-scan column chunks
     int mode, cap;

@@ -9,6 +9,7 @@ device buffers, pinned staging and the stream handle.
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from abc import ABC, abstractmethod
 from typing import Dict, Optional, Tuple
 
@@ -55,6 +56,11 @@ def make_params(extractor_params: Optional[dict], *, pyramid: bool):
     return p, w
 
 
+def copy_params(p: N.SfmExtractParams) -> N.SfmExtractParams:
+    """A private copy of a parameter struct (the weight pointer is shared; keep its owner alive)."""
+    return N.SfmExtractParams.from_buffer_copy(p)
+
+
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -96,6 +102,9 @@ def extract_batch_device(images: torch.Tensor, params: N.SfmExtractParams, *, wa
                     raise ValueError(f"out[{k!r}] must be contiguous with leading dimension {B}")
             cap = out['x'].shape[1]
         ptr = lambda k: out[k].data_ptr() if k in out else None
+        # a plateau image is retried on a private copy of the parameters: the caller's struct may be shared
+        # between threads (Runner.py:186-191 runs extractors from an 8-thread pool) and must not change under them
+        params = copy_params(params)
         for attempt in range(2):
             nbytes = L.sfm_extract_workspace_bytes(B, H, W, C.byref(params))
             if nbytes == 0:
@@ -127,9 +136,29 @@ def check_extract_status(result: Dict[str, torch.Tensor]) -> bool:
     return True if f is None else int(f.cpu()[0]) == 0
 
 
+_staging = threading.local()
+
+
 def _to_device(image: np.ndarray) -> torch.Tensor:
+    """numpy image -> CUDA tensor through a pinned staging buffer kept per thread and shape (pinning a fresh
+    buffer on every class call cost more than the extraction itself: cudaHostAlloc is a device-wide sync)."""
     a = np.ascontiguousarray(image, dtype=np.float32)
-    return torch.from_numpy(a).pin_memory().to('cuda', non_blocking=True)
+    cache = getattr(_staging, 'bufs', None)
+    if cache is None:
+        cache = _staging.bufs = {}
+    ent = cache.get(a.shape)
+    if ent is None:
+        if len(cache) >= 4:                       # a handful of shapes per thread is the working set of a run
+            cache.pop(next(iter(cache)))
+        ent = cache[a.shape] = [torch.empty(a.shape, dtype=torch.float32).pin_memory(), None]
+    buf, ev = ent
+    if ev is not None:
+        ev.synchronize()                          # the previous copy out of this buffer has finished
+    buf.numpy()[...] = a
+    dev = buf.to('cuda', non_blocking=True)
+    ent[1] = torch.cuda.Event()
+    ent[1].record()
+    return dev
 
 
 class FeatureExtractor(ABC):

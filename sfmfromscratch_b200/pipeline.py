@@ -268,7 +268,8 @@ class FeaturePipeline:
                 pairs = torch.from_numpy(inv.reshape(-1, 2).astype(np.int32)).to(desc_all.device, non_blocking=True)
         return match_batch_device(desc_all, counts_all, pairs, self.ratio_threshold, cap=cap)
 
-    def run_host(self, host_images: torch.Tensor, pairs_global: np.ndarray, host_out: dict, chunk: int = 8):
+    def run_host(self, host_images: torch.Tensor, pairs_global: np.ndarray, host_out: dict, chunk: int = 8,
+                 _params=None):
         """The hot path end to end from HOST buffers: `host_images` is a pinned
         float32 [B, H, W] tensor, `host_out` holds pinned result tensors
         (x, y, desc, count [, matches, conf, mcount]).  The batch is cut into
@@ -279,7 +280,8 @@ class FeaturePipeline:
         images finish -- with ~25 launches per chunk the host enqueue rate, not the tail, becomes the
         limit: 6.2-6.6 ms against 5.9 ms.)  Returns this rank's pair list, in the order of the rows of
         host_out['matches'], after everything has landed in `host_out`."""
-        from .extractor import check_extract_status, extract_batch_device
+        from .extractor import check_extract_status, copy_params, extract_batch_device
+        params = self.params if _params is None else _params
         dev = torch.device('cuda', torch.cuda.current_device())
         main = torch.cuda.current_stream()
         if not hasattr(self, '_s_in'):
@@ -304,7 +306,7 @@ class FeaturePipeline:
         flags = []
         for (c0, c1), ev in zip(bounds, ready):
             main.wait_event(ev)
-            res = extract_batch_device(imgs[c0:c1], self.params, want_aux=False, check=False,
+            res = extract_batch_device(imgs[c0:c1], params, want_aux=False, check=False,
                                        out={k: v[c0:c1] for k, v in full.items()})
             flags.append(res)
             done = torch.cuda.Event()
@@ -325,9 +327,13 @@ class FeaturePipeline:
             t.record_stream(self._s_in); t.record_stream(self._s_out)
         main.synchronize()
         if not all(check_extract_status(r) for r in flags):
-            # plateau image somewhere in the batch: redo it with full-size candidate buffers
-            self.params.cand_full = 1
-            return self.run_host(host_images, pairs_global, host_out, chunk)
+            # plateau image somewhere in the batch: redo it ONCE with full-size candidate buffers, on a private
+            # copy of the parameters (self.params is shared with other threads and with later calls)
+            if params.cand_full:
+                raise RuntimeError("candidate buffer overflow with full-size buffers")
+            retry = copy_params(params)
+            retry.cand_full = 1
+            return self.run_host(host_images, pairs_global, host_out, chunk, _params=retry)
         return mine
 
     def stream_host(self, host_images: torch.Tensor, pairs_global: np.ndarray, host_out: dict, chunk: int = 8):
@@ -347,7 +353,8 @@ class FeaturePipeline:
         cap = host_out['x'].shape[1]
         key = (B, H, W, cap, dev.index)
         if getattr(self, '_slots_key', None) != key:
-            self.drain()
+            ok = self.drain()                                   # the batches still in flight use the old slots
+            self._overflow = not ok                             # ... and their overflow report must survive the re-key
             i32 = dict(dtype=torch.int32, device=dev)
             self._slots = [{'imgs': torch.empty((B, H, W), dtype=torch.float32, device=dev),
                             'x': torch.empty((B, cap), **i32), 'y': torch.empty((B, cap), **i32),
