@@ -1,6 +1,8 @@
-"""configs[4] data on ONE GPU: every pair matched with and without the ratio prune / rejection, per-pair
-match counts compared on the device; pairs that differ are re-run in SFM_MATCH_EXACT mode to say which
-setting is right.  python scripts/check_config5.py [--images 512] [--ranks 8]"""
+"""configs[4] data on ONE GPU: every pair matched with and without the ratio prune / rejection (or, with
+--exact-all, by the tensor-core path and by the exact float32 scan); per pair the match COUNT, every matched
+(row, index) and every confidence (bitwise) are compared on the device -- both paths emit in the canonical
+(confidence, row) order, so the comparison is element-wise.  Pairs that differ are re-run in SFM_MATCH_EXACT
+mode to say which setting is right.  python scripts/check_config5.py [--images 512] [--ranks 8] [--exact-all]"""
 import argparse
 import os
 import sys
@@ -14,6 +16,16 @@ from sfmfromscratch_b200 import _native as N  # noqa: E402
 from sfmfromscratch_b200 import pipeline as PL  # noqa: E402
 from sfmfromscratch_b200.matcher import match_batch_device, match_workspace  # noqa: E402
 from scripts.run_config5 import synth_block  # noqa: E402
+
+
+def differing_pairs(r0, r1):
+    """Pairs whose results differ in count, in any matched (row, index) or in any confidence bit (device-side)."""
+    m0, c0, n0 = r0[0], r0[1], r0[2]
+    m1, c1, n1 = r1[0], r1[1], r1[2]
+    live = torch.arange(m0.shape[1], device=m0.device)[None, :] < torch.minimum(n0, n1)[:, None]
+    idx_bad = ((m0 != m1).any(dim=2) & live).any(dim=1)
+    conf_bad = ((c0.view(torch.int32) != c1.view(torch.int32)) & live).any(dim=1)
+    return torch.nonzero((n0 != n1) | idx_bad | conf_bad).flatten().tolist()
 
 
 def main():
@@ -43,7 +55,7 @@ def main():
             r0 = [x.clone() for x in r0]
             r1 = match_batch_device(desc, counts, pc, 0.8, cap=a.n, ws=ws, prepared=True, mode=N.SFM_MATCH_EXACT)
             tot[0] += int(r0[2].sum()); tot[1] += int(r1[2].sum())
-            for q in torch.nonzero(r0[2] != r1[2]).flatten().tolist():
+            for q in differing_pairs(r0, r1):
                 nbad += 1
                 k0, k1 = int(r0[2][q]), int(r1[2][q])
                 s0 = {(int(x), int(y)): float(z) for (x, y), z in zip(r0[0][q, :k0].cpu().numpy(), r0[1][q, :k0].cpu().numpy())}
@@ -52,7 +64,7 @@ def main():
                       "only exact", [(k, s1[k]) for k in set(s1) - set(s0)], flush=True)
             if (c0 // a.chunk) % 32 == 0:
                 print("chunk", c0, "totals", tot, "differing pairs", nbad, flush=True)
-        print("matches auto", tot[0], "exact", tot[1], "pairs with different counts", nbad)
+        print("matches auto", tot[0], "exact", tot[1], "pairs whose counts, indices or confidences differ", nbad)
         return
     tot = [0, 0]
     bad = []
@@ -62,12 +74,11 @@ def main():
         for k, knob in enumerate((0, N.SFM_MATCH_NO_PRUNE)):
             m, c, cnt = match_batch_device(desc, counts, pc, 0.8, mode=N.SFM_MATCH_AUTO | knob, cap=a.n, ws=ws,
                                            prepared=(c0 > 0 or k > 0))
-            res.append(cnt.clone())
+            res.append((m.clone(), c.clone(), cnt.clone()))
             tot[k] += int(cnt.sum())
-        diff = torch.nonzero(res[0] != res[1]).flatten().tolist()
-        for q in diff:
-            bad.append((c0 + q, int(res[0][q]), int(res[1][q])))
-    print("matches with prune", tot[0], "without", tot[1], "pairs that differ", len(bad))
+        for q in differing_pairs(res[0], res[1]):
+            bad.append((c0 + q, int(res[0][2][q]), int(res[1][2][q])))
+    print("matches with prune", tot[0], "without", tot[1], "pairs whose counts, indices or confidences differ", len(bad))
     for (pi, n_p, n_np) in bad[:40]:
         pc = pairs[pi:pi + 1]
         m, c, cnt = match_batch_device(desc, counts, pc, 0.8, cap=a.n, mode=N.SFM_MATCH_EXACT)

@@ -209,12 +209,13 @@ class FeaturePipeline:
         self.rank, self.world, self.group = rank, world, group
         self.pair_block = 64
 
-    def extract(self, images: torch.Tensor, deferred_check: bool = False):
+    def extract(self, images: torch.Tensor, deferred_check: bool = False, out: Optional[dict] = None):
         """Extraction of a resident batch.  By default the candidate-overflow flag is read back right
         away (a host wait per call).  With `deferred_check` the flags accumulate on the device -- nothing
-        waits, the host keeps enqueueing -- and `overflow_since_last_check()` reads them once."""
+        waits, the host keeps enqueueing -- and `overflow_since_last_check()` reads them once.  `out` may hold
+        preallocated result tensors (x, y, count, desc), e.g. slices of a shard-wide table filled batch by batch."""
         from .extractor import extract_batch_device
-        out = extract_batch_device(images, self.params, want_aux=False, check=not deferred_check)
+        out = extract_batch_device(images, self.params, want_aux=False, check=not deferred_check, out=out)
         if deferred_check:
             if getattr(self, '_flag_acc', None) is None or self._flag_acc.device != images.device:
                 self._flag_acc = torch.zeros((1,), dtype=torch.int32, device=images.device)

@@ -45,6 +45,47 @@ def synth_image(h: int, w: int, seed: int, sigma: float = 2.0) -> np.ndarray:
     return ((a - lo) / (hi - lo)).astype(np.float32)
 
 
+def sequence_canvas(h: int, w: int, total: int, seed: int = 7, step: int = 24, sigma: float = 2.0) -> np.ndarray:
+    """The blurred-noise canvas (float64, h x (w + step * (total - 1)), in [0, 1]) a `total`-frame synthetic
+    video pans over; depends on (h, w, total, seed, step) only, so every rank computes the same one."""
+    cw = w + step * (total - 1)
+    rng = np.random.default_rng(seed)
+    a = rng.random((h, cw), dtype=np.float64)
+    taps = _gauss_taps(sigma)
+    a = _blur_axis(_blur_axis(a, taps, 0), taps, 1)
+    lo, hi = a.min(), a.max()
+    return (a - lo) / (hi - lo)
+
+
+def sequence_frame(canvas: np.ndarray, f: int, w: int, seed: int = 7, step: int = 24, noise: float = 0.005) -> np.ndarray:
+    """Frame `f` of the video over `canvas`: the window starting `f * step` columns in, plus the frame's own
+    N(0, noise) sensor noise (generator seeded by the frame index), clipped to [0, 1].  float32 (h, w)."""
+    h = canvas.shape[0]
+    r = np.random.default_rng(1000 * seed + 17 + f)
+    return np.clip(canvas[:, f * step: f * step + w] + r.normal(0.0, noise, size=(h, w)), 0.0, 1.0).astype(np.float32)
+
+
+def frame_sequence(h: int, w: int, first: int, count: int, total: int, seed: int = 7, step: int = 24,
+                   noise: float = 0.005, threads: int = 1) -> np.ndarray:
+    """Frames `first .. first + count - 1` of a `total`-frame synthetic video: a camera panning over one
+    blurred-noise canvas by `step` pixels per frame.  Consecutive frames overlap by (w - step) columns, so the
+    consecutive-pair matching the reference does (Runner.py:183-191) finds true correspondences, as it does
+    on real footage.  float32 (count, h, w)."""
+    canvas = sequence_canvas(h, w, total, seed, step)
+    out = np.empty((count, h, w), np.float32)
+
+    def one(k):
+        out[k] = sequence_frame(canvas, first + k, w, seed, step, noise)
+    if threads > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(one, range(count)))
+    else:
+        for k in range(count):
+            one(k)
+    return out
+
+
 def second_view(img: np.ndarray, seed: int, noise: float = 0.005) -> np.ndarray:
     """Affine warp [[1, .02, 3.5], [-.02, 1, -2.25]] (bilinear, reflect border)
     plus N(0, noise) -- the second camera of the synthetic two-view pair."""

@@ -7,11 +7,17 @@ Keypoints   X, Y identical element for element.  The reference orders a level
 Descriptors same keypoint => |delta| <= DESC_ATOL for every element.  The
             reference itself is only reproducible to 1 ulp here: its
             np.linalg.norm goes through BLAS sdot, whose summation order depends
-            on buffer alignment.  The CUDA path evaluates arctan2 in double and
+            on buffer alignment.  There is NO quota of descriptors that may
+            differ.  A descriptor over the tolerance fails the test unless the
+            test PROVES the one stated exemption for that keypoint
+            (DescriptorExplainer): the CUDA path evaluates arctan2 in double and
             rounds once, numpy's float32 arctan2 is a few-ulp SVML routine, so a
-            sample lying within a few ulp of a histogram edge can land in the
-            neighbouring bin: at most DESC_FLIP_FRAC of the keypoints (and never
-            fewer than 1 allowed) may exceed the tolerance.
+            window sample whose orientation lies within 4 float32 ulp of a
+            histogram edge (36-bin grid, or 8-bin grid after the dominant
+            orientation is subtracted) can land in the neighbouring bin, and a
+            36-bin histogram whose two largest totals agree to 1e-5 relative can
+            elect the other one (SURVEY.md section 8c "parity rules").  On the
+            seeded generic images no keypoint needs it and the tests assert that.
 Matches     for identical descriptor inputs the (row, index, confidence)
             triples are bit-identical; order is compared after sorting runs of
             equal confidence by row (the reference's tie order is arbitrary).
@@ -22,7 +28,8 @@ Matches     for identical descriptor inputs the (row, index, confidence)
 import numpy as np
 
 DESC_ATOL = 3.0e-7        # ~2.5 ulp at 1.0
-DESC_FLIP_FRAC = 0.004
+EDGE_ULPS = 4             # a sample this close (float32 ulp of its orientation) to a bin edge may change bins
+TOP2_REL = 1.0e-5         # 36-bin totals this close (relative) may elect either bin as the dominant orientation
 RATIO_EDGE = 1.0e-5
 
 
@@ -34,17 +41,77 @@ def assert_keypoints_equal(X, Y, Xr, Yr):
     assert bad.size == 0, f"{bad.size} keypoints differ, first at {bad[:5]}"
 
 
-def assert_descriptors_close(D, Dr, atol=DESC_ATOL, flip_frac=DESC_FLIP_FRAC):
+class DescriptorExplainer:
+    """Finds, for keypoint i, the window sample that licenses a descriptor difference (see the module
+    docstring), or returns None.  Works from the image alone with the oracle's arithmetic: pyramid,
+    Sobel gradients, float32 magnitude and numpy arctan2, exactly what the reference hands np.histogram
+    (ScaleRotInvSIFT.py:24-31,45-76; NaiveSIFT.py:137-171)."""
+
+    def __init__(self, image, params=None, levels=None, level_x=None, level_y=None, pyramid=True):
+        from oracle import oracle as O
+        p = params or {}
+        self.rot = pyramid
+        L = p.get('pyramid_level', 4) if pyramid else 1
+        f = p.get('pyramid_scale_factor', 2) if pyramid else 1
+        self.pyr = O.build_pyramid(np.asarray(image, dtype=np.float32), L, f)
+        fw0 = p.get('feature_width', 16)
+        self.fw = [max(int(fw0 / f ** l), 3) if pyramid else fw0 for l in range(L)]
+        self.levels = np.zeros(len(level_x), np.int64) if levels is None else np.asarray(levels)
+        self.lx, self.ly = np.asarray(level_x), np.asarray(level_y)
+        self._grad = {}
+        self.e37 = np.linspace(-np.pi, np.pi, 37)
+        self.e9 = np.linspace(-np.pi, np.pi, 9)
+
+    def _maps(self, l):
+        if l not in self._grad:
+            from oracle import oracle as O
+            Ix, Iy = O.image_gradients(self.pyr[l])
+            self._grad[l] = (np.sqrt(Ix ** 2 + Iy ** 2), np.arctan2(Iy, Ix))
+        return self._grad[l]
+
+    def __call__(self, i):
+        l = int(self.levels[i])
+        x, y, hw = int(self.lx[i]), int(self.ly[i]), self.fw[l] // 2
+        magn, orient = self._maps(l)
+        fm = magn[y - hw + 1:y + hw + 1, x - hw + 1:x + hw + 1].ravel()
+        fo = orient[y - hw + 1:y + hw + 1, x - hw + 1:x + hw + 1].ravel()
+        tol = EDGE_ULPS * np.spacing(np.abs(fo)).astype(np.float64)
+        rel = fo.astype(np.float64)
+        if self.rot:
+            hist, _ = np.histogram(fo, bins=self.e37, weights=fm)
+            top = np.sort(hist)[::-1]
+            if top[0] > 0 and (top[0] - top[1]) <= TOP2_REL * top[0]:
+                return f"36-bin top-2 totals {top[0]!r}, {top[1]!r} within {TOP2_REL} relative"
+            d = np.abs(rel[:, None] - self.e37[None, :])
+            k = np.argwhere((d <= tol[:, None]) & (fm[:, None] > 0))
+            if len(k):
+                return f"sample {int(k[0][0])} within {EDGE_ULPS} ulp of 36-bin edge {int(k[0][1])}"
+            rel = rel - (self.e37[np.argmax(hist)] + self.e37[np.argmax(hist) + 1]) / 2
+        d = np.abs(rel[:, None] - self.e9[None, :])
+        k = np.argwhere((d <= tol[:, None]) & (fm[:, None] > 0))
+        if len(k):
+            return f"sample {int(k[0][0])} within {EDGE_ULPS} ulp of 8-bin edge {int(k[0][1])}"
+        return None
+
+
+def assert_descriptors_close(D, Dr, explain=None, atol=DESC_ATOL):
+    """Every descriptor within `atol`, element-wise.  A descriptor over it must be licensed by `explain(i)`
+    (a DescriptorExplainer) -- without an explainer none may be.  Returns the number of licensed keypoints."""
     D, Dr = np.asarray(D), np.asarray(Dr)
     assert D.shape == Dr.shape, (D.shape, Dr.shape)
     if D.size == 0:
         return 0
     assert D.dtype == np.float32
-    err = np.abs(D.astype(np.float64) - Dr.astype(np.float64)).max(axis=1)
-    over = int((err > atol).sum())
-    allowed = max(1, int(np.ceil(flip_frac * len(err))))
-    assert over <= allowed, f"{over} of {len(err)} descriptors differ by more than {atol} (allowed {allowed}); worst {err.max()}"
-    return over
+    D2, Dr2 = np.atleast_2d(D), np.atleast_2d(Dr)
+    err = np.abs(D2.astype(np.float64) - Dr2.astype(np.float64)).max(axis=1)
+    over = np.nonzero(err > atol)[0]
+    licensed = 0
+    for i in over:
+        why = explain(int(i)) if explain is not None else None
+        assert why is not None, (f"descriptor {int(i)} of {len(err)} differs by {err[i]:.3g} (> {atol}) and no window sample lies "
+                                 f"within {EDGE_ULPS} ulp of a histogram edge ({len(over)} over tolerance in all)")
+        licensed += 1
+    return licensed
 
 
 def canonical_matches(matches, conf):
@@ -64,3 +131,20 @@ def assert_matches_identical(matches, conf, matches_ref, conf_ref):
     # the emitted order must already be ascending in confidence
     conf = np.asarray(conf)
     assert np.all(np.diff(conf) >= 0)
+
+
+def assert_matches_equivalent(matches, conf, matches_ref, conf_ref, thr, conf_atol=1.0e-6):
+    """End-to-end comparison, when the two sides' descriptors differ by DESC_ATOL: the matched (row, index) sets are
+    equal except for rows whose ratio lies within RATIO_EDGE of the threshold; rows on both sides agree in their
+    index and, within conf_atol, in their confidence.  Returns the number of threshold-edge rows."""
+    a = {int(r): (int(j), float(c)) for (r, j), c in zip(np.asarray(matches).reshape(-1, 2), np.asarray(conf).reshape(-1))}
+    b = {int(r): (int(j), float(c)) for (r, j), c in zip(np.asarray(matches_ref).reshape(-1, 2), np.asarray(conf_ref).reshape(-1))}
+    edge = 0
+    for r in set(a) ^ set(b):
+        c = (a.get(r) or b.get(r))[1]
+        assert abs(c - float(np.float32(thr))) <= RATIO_EDGE, f"row {r} matched on one side only with ratio {c} (threshold {thr})"
+        edge += 1
+    for r in set(a) & set(b):
+        assert a[r][0] == b[r][0], f"row {r}: index {a[r][0]} vs {b[r][0]}"
+        assert abs(a[r][1] - b[r][1]) <= conf_atol, f"row {r}: confidence {a[r][1]} vs {b[r][1]}"
+    return edge

@@ -24,7 +24,7 @@ def test_scale_rot_inv_sift(reference_modules, h, w, seed, params):
     r = fe.ScaleRotInvSIFT(img, params)
     o = O.ScaleRotInvSIFT(img, params)
     assert_keypoints_equal(*o.detect_keypoints(), *r.detect_keypoints())
-    assert_descriptors_close(o.extract_descriptors(), r.extract_descriptors(), atol=1.3e-7, flip_frac=0.0)
+    assert_descriptors_close(o.extract_descriptors(), r.extract_descriptors(), atol=1.3e-7)
 
 
 def test_naive_sift(reference_modules):
@@ -33,7 +33,7 @@ def test_naive_sift(reference_modules):
     r, o = fe.NaiveSIFT(img, {'num_interest_points': 200}), O.NaiveSIFT(img, {'num_interest_points': 200})
     assert_keypoints_equal(*o.detect_keypoints(), *r.detect_keypoints())
     assert np.array_equal(o.confidences, r.confidences)
-    assert_descriptors_close(o.extract_descriptors(), r.extract_descriptors(), atol=1.3e-7, flip_frac=0.0)
+    assert_descriptors_close(o.extract_descriptors(), r.extract_descriptors(), atol=1.3e-7)
 
 
 def test_harris_plateau_image(reference_modules):
