@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB = os.path.join(_HERE, "libsfmb200.so")
 SOURCES = ["api.cu", "extract.cu", "match.cu", "match_tc.cu", "ingest.cu", "ransac.cu", "assoc.cu"]
-HEADERS = ["common.cuh", "extract.cuh", "match.cuh", "ransac_math.cuh", os.path.join("..", "..", "include", "sfmb200.h")]
+HEADERS = ["common.cuh", "extract.cuh", "harris_stream.cuh", "tma.cuh", "match.cuh", "ransac_math.cuh", os.path.join("..", "..", "include", "sfmb200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-cudart", "static"]
 
