@@ -9,10 +9,10 @@
 //     chains run at 85-89 %, but
 //   * 4 rows per thread in a tile kernel leaves 8 warps per SM, too few to hide the tile load, the Sobel/product
 //     phase and the barriers between them: measured slower (0.89 ms against 0.77 per 32 x 1080p).
-// So the phases are decoupled instead of interleaved by occupancy.  One persistent CTA per SM, 12 warps:
-//   warps 0-7   CONSUMERS: the window stage only, 4 rows x 8 px per thread (a warp = one 64 x 16 band), product rows
+// So the phases are decoupled instead of interleaved by occupancy.  One persistent CTA per SM, 16 warps:
+//   warps 8-15  CONSUMERS: the window stage only, 4 rows x 8 px per thread (a warp = one 64 x 16 band), product rows
 //               read from a shared-memory ring, R stored from registers, first radix-select histogram;
-//   warps 8-11  PRODUCERS: Sobel + the three products (NaiveSIFT.py:61-64) of one 16-row chunk at a time, from a
+//   warps 0-7   PRODUCERS (two groups of four, alternating chunks): Sobel + the three products (NaiveSIFT.py:61-64) of one 16-row chunk at a time, from a
 //               TMA-staged image tile (cp.async.bulk.tensor, zero fill outside the image == BORDER_CONSTANT, issued
 //               ISTAGES - 2 chunks ahead by the producer warps in turn) into the ring; they also emit the strip's part
 //               of pyramid level l+1 (the exact 2x2 mean) from the tile they hold.
@@ -27,10 +27,12 @@ namespace hs {
 
 constexpr int SW = 64;                 // strip width
 constexpr int BH = 16;                 // band height == chunk height
-constexpr int NCONS = 8, NPROD = 4;    // consumer / producer warps: two + one per SM sub-partition
-constexpr int THREADS = 32 * (NCONS + NPROD);
+constexpr int NCONS = 8, NPROD = 4;    // consumer warps; producer warps PER GROUP
+constexpr int NGROUP = 2;              // producer groups: group g computes the chunks q with q % NGROUP == g
+constexpr int THREADS = 32 * (NCONS + NPROD * NGROUP);
+constexpr int REGS_PROD = 80, REGS_CONS = 168;   // setmaxnreg: 16 warps x 128 registers re-dealt between the roles
 constexpr int RING = 12;               // product chunks in flight (8 bands being read need 9)
-constexpr int ISTAGES = 7;             // staged image tiles: the TMA loads run this many chunks ahead of the producers
+constexpr int ISTAGES = 8;             // staged image tiles: the TMA loads run this many chunks ahead of the producers
 
 template <int G> struct Cfg {
     static constexpr int R = G / 2;
@@ -107,7 +109,11 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
     __syncthreads();
     if (g.n0 >= g.n1) return;
 
-    if (warp < hs::NCONS) {
+    // Producers take the LOWEST warp ids: the warp scheduler favours older warps, and with the consumers in front the
+    // producers only ran in the gaps both consumers of their sub-partition left (2 270 clk per chunk: the bottleneck).
+    if (warp >= hs::NPROD * hs::NGROUP) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(hs::REGS_CONS));
+        const int cw = warp - hs::NPROD * hs::NGROUP;      // consumer warp 0 .. 7
         // ================================================================== consumers
         const int tx = lane & 7, ty = lane >> 3;
         int coff[C::NCH];
@@ -116,7 +122,7 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
         int b0i, s0i, k0i;
         hs::decompose(g, g.n0, b0i, s0i, k0i);
         int epoch = 0;                                     // images of this CTA's range whose histogram has been flushed
-        const int ct = t;                                  // 0 .. 255 among the consumers
+        const int ct = t - 32 * hs::NPROD * hs::NGROUP;    // 0 .. 255 among the consumers
         auto flush = [&](int b) {
             // every consumer warp has finished image b's bands: push the shared histogram to the segment's and clear it
             bar_sync(1, 32 * hs::NCONS);
@@ -133,7 +139,7 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
             }
             bar_sync(1, 32 * hs::NCONS);
         };
-        for (int n = g.n0 + warp; ; n += hs::NCONS) {
+        for (int n = g.n0 + cw; ; n += hs::NCONS) {
             int b, s, k;
             const bool live = n < g.n1;
             hs::decompose(g, live ? n : g.n1 - 1, b, s, k);
@@ -242,11 +248,13 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
         }
     } else {
         // ================================================================== producers
-        const int pw = warp - hs::NCONS;                   // 0 .. 3
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(hs::REGS_PROD));
+        const int pw = warp & (hs::NPROD - 1);             // 0 .. 3 inside the group
+        const int grp = warp / hs::NPROD;
         const LevelInfo& nx = P.lv[(l + 1 < P.L) ? l + 1 : l];
-        constexpr int AHEAD = hs::ISTAGES - 2;             // a tile is requested this many chunks before it is used
-        // the chunk sequence twice: `c` is the chunk being computed, `f` the one being fetched
-        struct Cur { int n, b, s, k, extra, q; };
+        // A cursor over the chunk sequence of this CTA's band range.  Chunk q lives in ring slot q % RING and image
+        // stage q % ISTAGES; the phase bits flip at every wrap.  Advancing costs a handful of integer instructions.
+        struct Cur { int n, b, s, k, extra, slot, sph, st, iph; };
         auto last_in_run = [&](const Cur& c) { return (c.k == g.K - 1) || (c.n == g.n1 - 1); };
         auto advance = [&](Cur& c) {
             if (c.extra == 0 && last_in_run(c)) c.extra = 1;
@@ -254,44 +262,50 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
                 c.extra = 0; ++c.n;
                 if (++c.k == g.K) { c.k = 0; if (++c.s == g.S) { c.s = 0; ++c.b; } }
             }
-            ++c.q;
+            if (++c.slot == hs::RING) { c.slot = 0; c.sph ^= 1; }
+            if (++c.st == hs::ISTAGES) { c.st = 0; c.iph ^= 1; }
         };
-        auto fetch = [&](const Cur& f) {                   // one producer warp per chunk, in turn
-            if ((f.q & (hs::NPROD - 1)) != pw) return;
-            const int st = f.q % hs::ISTAGES;
-            if (f.q >= hs::ISTAGES) mbar_wait(bar_iempty(st), (uint32_t)(((f.q / hs::ISTAGES) - 1) & 1));
-            if (lane == 0) {
-                mbar_expect_tx(bar_ifull(st), (uint32_t)(C::ITILE * sizeof(float)));
-                tma_load_3d(smem_u32(s_img + (size_t)st * C::ISTRIDE), &tmap, bar_ifull(st), f.s * hs::SW - C::RA,
-                            (f.k + f.extra) * hs::BH - C::R - 1, f.b);
-            }
-            __syncwarp();
-        };
-        Cur c, f;
+        Cur c;
         hs::decompose(g, g.n0, c.b, c.s, c.k);
-        c.n = g.n0; c.extra = 0; c.q = 0;
-        f = c;
-        for (int i = 0; i < AHEAD && f.n < g.n1; ++i) { fetch(f); advance(f); }
-        for (; c.n < g.n1; advance(c)) {
-            if (f.n < g.n1) { fetch(f); advance(f); }
-            const int q = c.q, kc = c.k + c.extra;
+        c.n = g.n0; c.extra = 0; c.slot = 0; c.sph = 0; c.st = 0; c.iph = 0;
+        for (int i = 0; i < grp && c.n < g.n1; ++i) advance(c);          // group g starts at chunk g
+        Cur f = c;                                                       // the chunk being fetched: ISTAGES / NGROUP of this group's ahead
+        int fturn = 0;                                                   // the group's warps issue the loads in turn
+        auto fetch = [&]() {
+            if (f.n >= g.n1) return;
+            if (fturn == pw) {
+                // the stage was this group's, ISTAGES chunks ago: wait until its four warps have let go of it (a fresh
+                // barrier reports the phase before its first as complete)
+                mbar_wait(bar_iempty(f.st), (uint32_t)(f.iph ^ 1));
+                if (lane == 0) {
+                    mbar_expect_tx(bar_ifull(f.st), (uint32_t)(C::ITILE * sizeof(float)));
+                    tma_load_3d(smem_u32(s_img + (size_t)f.st * C::ISTRIDE), &tmap, bar_ifull(f.st), f.s * hs::SW - C::RA,
+                                (f.k + f.extra) * hs::BH - C::R - 1, f.b);
+                }
+                __syncwarp();
+            }
+            fturn = (fturn + 1) & (hs::NPROD - 1);
+#pragma unroll
+            for (int i = 0; i < hs::NGROUP; ++i) if (f.n < g.n1) advance(f);
+        };
+#pragma unroll 1
+        for (int i = 0; i < hs::ISTAGES / hs::NGROUP - 1; ++i) fetch();
+#pragma unroll 1
+        while (c.n < g.n1) {
+            fetch();
+            const int kc = c.k + c.extra;
             const bool first_in_run = (c.k == 0) || (c.n == g.n0);
             const int rows = c.extra ? 2 * C::R : hs::BH;          // the run's closing chunk: only its first 2R rows are read
-            const int slot = q % hs::RING, st = q % hs::ISTAGES;
-            if (q >= hs::RING) mbar_wait(bar_empty(slot), (uint32_t)(((q / hs::RING) - 1) & 1));
-            mbar_wait(bar_ifull(st), (uint32_t)((q / hs::ISTAGES) & 1));
-            const float* tile = s_img + (size_t)st * C::ISTRIDE;
-            float* dst = s_ring + (size_t)slot * C::SLOT;
+            mbar_wait(bar_empty(c.slot), (uint32_t)(c.sph ^ 1));   // (a fresh barrier reports the phase before its first as complete)
+            mbar_wait(bar_ifull(c.st), (uint32_t)c.iph);
+            const float* tile = s_img + (size_t)c.st * C::ISTRIDE;
+            float* dst = s_ring + (size_t)c.slot * C::SLOT;
             const int x0 = c.s * hs::SW, y0 = kc * hs::BH;         // product row py is image row y0 - R + py
-            // PCH * BH = 288 strip tasks of 4 pixels: two rounds of 128 and a third of 32 that rotates over the warps
+            // PCH * BH = 288 strip tasks of 4 pixels: two per thread, and a third for one warp of the group in turn
             const int ntask = C::PCH * rows;
-            for (int round = 0; round * 32 * hs::NPROD < ntask; ++round) {
-                const int wsel = (round == 2) ? ((pw + q) & (hs::NPROD - 1)) : pw;
-                const int i = round * 32 * hs::NPROD + wsel * 32 + lane;
-                if (i >= ntask) continue;
-                const int py = i / C::PCH, c4 = i - py * C::PCH;
-                const int cc = 4 * c4;
-                const float* ip = tile + py * C::IPITCH + cc + C::OFF;
+            auto task = [&](int ti) {
+                const int py = ti / C::PCH, c4 = ti - py * C::PCH;
+                const float* ip = tile + py * C::IPITCH + 4 * c4 + C::OFF;
                 float w0[6], w1[6], w2[6];
                 if constexpr ((C::OFF & 3) == 0) {
                     const float4 a = *reinterpret_cast<const float4*>(ip);
@@ -317,7 +331,7 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
                     xy[e] = __fmul_rn(sx, sy);
                 }
                 // outside the image the PRODUCTS are zero: the window filter pads the product planes, not the image
-                const int gy = y0 - C::R + py, gx0 = x0 - C::R + cc;
+                const int gy = y0 - C::R + py, gx0 = x0 - C::R + 4 * c4;
                 if (!(gy >= 0 && gy < g.H && gx0 >= 0 && gx0 + 3 < g.W)) {
                     const bool rowok = (gy >= 0 && gy < g.H);
 #pragma unroll
@@ -328,9 +342,13 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
                 *reinterpret_cast<float4*>(o) = make_float4(xx[0], xx[1], xx[2], xx[3]);
                 *reinterpret_cast<float4*>(o + C::PLANE) = make_float4(xy[0], xy[1], xy[2], xy[3]);
                 *reinterpret_cast<float4*>(o + 2 * C::PLANE) = make_float4(yy[0], yy[1], yy[2], yy[3]);
-            }
+            };
+            const int t0i = pw * 32 + lane;
+            if (t0i < ntask) task(t0i);
+            if (t0i + 32 * hs::NPROD < ntask) task(t0i + 32 * hs::NPROD);
+            if (((pw + c.slot) & (hs::NPROD - 1)) == 0 && 2 * 32 * hs::NPROD + lane < ntask) task(2 * 32 * hs::NPROD + lane);   // warp-uniform
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_full(slot));
+            if (lane == 0) mbar_arrive(bar_full(c.slot));
             if (fuse_next) {
                 // ScaleRotInvSIFT.py:109-115 -> cv2.resize at an exact halving -> INTER_AREA 2x2 mean, from the staged tile.
                 // A run over bands [ka, kb] owns image rows [16 ka, 16 (kb + 1)); its chunk kc holds image rows
@@ -339,24 +357,25 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
                 float* dstl = P.pyr + (size_t)c.b * P.pyr_stride + nx.img_off;
                 const int ylo = (c.extra == 0 && first_in_run) ? kc * hs::BH : kc * hs::BH - C::EMIT;
                 const int yhi = c.extra ? kc * hs::BH : kc * hs::BH - C::EMIT + hs::BH;      // exclusive
-                for (int i = pw * 32 + lane; i < (hs::BH / 2) * (hs::SW / 4); i += 32 * hs::NPROD) {
-                    const int pr = i / (hs::SW / 4), oq = i - pr * (hs::SW / 4);
-                    const int y = kc * hs::BH - C::EMIT + 2 * pr;                      // image row of the pair's upper row
-                    const int oy = y >> 1, gx = (x0 >> 1) + 2 * oq;
-                    if (y >= ylo && y < yhi && oy < nx.H && gx < nx.W) {
-                        const float* p = tile + (y - (kc * hs::BH - C::R - 1)) * C::IPITCH + C::RA + 4 * oq;
-                        const float4 u = *reinterpret_cast<const float4*>(p);
-                        const float4 d = *reinterpret_cast<const float4*>(p + C::IPITCH);
-                        const float o0 = __fmul_rn(__fadd_rn(__fadd_rn(u.x, u.y), __fadd_rn(d.x, d.y)), 0.25f);
-                        const float o1 = __fmul_rn(__fadd_rn(__fadd_rn(u.z, u.w), __fadd_rn(d.z, d.w)), 0.25f);
-                        float* o = dstl + (size_t)oy * nx.W + gx;
-                        if (gx + 1 < nx.W && (nx.W & 1) == 0) *reinterpret_cast<float2*>(o) = make_float2(o0, o1);
-                        else { o[0] = o0; if (gx + 1 < nx.W) o[1] = o1; }
-                    }
+                const int i = pw * 32 + lane;
+                const int pr = i / (hs::SW / 4), oq = i - pr * (hs::SW / 4);
+                const int y = kc * hs::BH - C::EMIT + 2 * pr;                          // image row of the pair's upper row
+                const int oy = y >> 1, gx = (x0 >> 1) + 2 * oq;
+                if (y >= ylo && y < yhi && oy < nx.H && gx < nx.W) {
+                    const float* pp = tile + (y - (kc * hs::BH - C::R - 1)) * C::IPITCH + C::RA + 4 * oq;
+                    const float4 u = *reinterpret_cast<const float4*>(pp);
+                    const float4 d = *reinterpret_cast<const float4*>(pp + C::IPITCH);
+                    const float o0 = __fmul_rn(__fadd_rn(__fadd_rn(u.x, u.y), __fadd_rn(d.x, d.y)), 0.25f);
+                    const float o1 = __fmul_rn(__fadd_rn(__fadd_rn(u.z, u.w), __fadd_rn(d.z, d.w)), 0.25f);
+                    float* o = dstl + (size_t)oy * nx.W + gx;
+                    if (gx + 1 < nx.W && (nx.W & 1) == 0) *reinterpret_cast<float2*>(o) = make_float2(o0, o1);
+                    else { o[0] = o0; if (gx + 1 < nx.W) o[1] = o1; }
                 }
                 __syncwarp();
             }
-            if (lane == 0) mbar_arrive(bar_iempty(st));
+            if (lane == 0) mbar_arrive(bar_iempty(c.st));
+#pragma unroll
+            for (int i = 0; i < hs::NGROUP; ++i) if (c.n < g.n1) advance(c);
         }
     }
 }
