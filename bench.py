@@ -473,9 +473,8 @@ def run_ours(args):
     # exchange is an all-gather of the ONE descriptor block per rank the neighbouring shard needs (PairPlan)
     plan = pipe.pair_plan(pairs_global, per)
     n_my_pairs = int(len(plan.mine))
-    i32 = dict(dtype=torch.int32, device=dev)
-    shard = {'x': torch.empty((per, cap), **i32), 'y': torch.empty((per, cap), **i32), 'count': torch.empty((per,), **i32),
-             'desc': torch.empty((per, cap, 128), dtype=torch.float32, device=dev)}
+    # this rank's result tables; the descriptor table carries the exchange's slots behind the rank's own blocks
+    shard = pipe.shard_tables(plan, cap, dev)
     bounds = [(b0, min(b0 + batch, per)) for b0 in range(0, per, batch)]
 
     def step():
@@ -517,7 +516,7 @@ def run_ours(args):
     value = pixels_per_step / (ms_per_step * 1e-3) / 1e6
     mcount = step()
     matches_per_pair = float(mcount[2].float().mean().item()) if mcount is not None else None
-    kp_per_image = float(shard['count'].float().mean().item())
+    kp_per_image = float(shard['count'][:per].float().mean().item())
 
     # ---- the same step for >= 2 s: what the clocks do under seconds of load
     n_sust = max(args.steps, int(math.ceil(2200.0 / ms_per_step)))

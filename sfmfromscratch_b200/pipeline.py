@@ -165,21 +165,28 @@ def exchange_for(plan: PairPlan, desc: torch.Tensor, counts: torch.Tensor, group
     idx = plan.send_idx_dev(desc.device)
     world = dist.get_world_size(group)
     K, n_own = plan.K, len(plan.send_local)
+    own_d, own_c = desc[:plan.per], counts[:plan.per]           # (the table may carry the exchange slots behind them)
     blk = int(np.prod(desc.shape[1:]))                         # floats per descriptor block
     # ONE collective: the K blocks and their K counts travel in one packed float32 buffer (the counts as raw int32
     # bits behind the blocks); two small all-gathers cost their launch latency twice (~0.05 ms per step at N = 8)
     kpad = (K + 3) // 4 * 4
     send = torch.zeros((K * blk + kpad,), dtype=torch.float32, device=desc.device)
     if n_own:
-        send[:n_own * blk].view(n_own, *desc.shape[1:]).copy_(desc.index_select(0, idx))
-        send[K * blk:K * blk + n_own].view(torch.int32).copy_(counts.index_select(0, idx).to(torch.int32))
+        send[:n_own * blk].view(n_own, *desc.shape[1:]).copy_(own_d.index_select(0, idx))
+        send[K * blk:K * blk + n_own].view(torch.int32).copy_(own_c.index_select(0, idx).to(torch.int32))
     got = torch.empty((world, K * blk + kpad), dtype=torch.float32, device=desc.device)
     try:
         dist.all_gather_into_tensor(got, send, group=group)
     except (RuntimeError, NotImplementedError):                # backends without the fused form
         dist.all_gather(list(got.unbind(0)), send, group=group)
-    got_d = got[:, :K * blk].reshape(world * K, *desc.shape[1:])            # strided view; the cat below makes the table dense
+    got_d = got[:, :K * blk].reshape(world * K, *desc.shape[1:])            # strided view
     got_c = got[:, K * blk:K * blk + K].view(torch.int32).reshape(world * K).to(counts.dtype)
+    if desc.shape[0] == plan.per + world * K:
+        # the caller's table already has the slots behind this rank's blocks (FeaturePipeline.shard_tables): only the
+        # gathered blocks move (world * K blocks instead of a copy of the whole shard, 164 MB per step at N = 2)
+        desc[plan.per:].copy_(got_d)
+        counts[plan.per:].copy_(got_c)
+        return desc, counts
     return torch.cat([desc, got_d], dim=0), torch.cat([counts, got_c], dim=0)
 
 
@@ -246,6 +253,16 @@ class FeaturePipeline:
 
     def exchange(self, desc: torch.Tensor, counts: torch.Tensor):
         return gather_descriptors(desc, counts, self.group)
+
+    def shard_tables(self, plan: PairPlan, cap: int, device) -> dict:
+        """Result tables of this rank's `plan.per` images (x, y, count, desc) whose descriptor / count tables carry, behind
+        the rank's own blocks, the slots the exchange of `plan` fills (policy "local": world * K blocks) -- extraction
+        writes rows [0, per), `match_plan` gathers in place and nothing is concatenated per step."""
+        extra = plan.world * plan.K if (plan.policy == "local" and plan.world > 1) else 0
+        i32 = dict(dtype=torch.int32, device=device)
+        return {'x': torch.empty((plan.per, cap), **i32), 'y': torch.empty((plan.per, cap), **i32),
+                'count': torch.zeros((plan.per + extra,), **i32),
+                'desc': torch.empty((plan.per + extra, cap, 128), dtype=torch.float32, device=device)}
 
     def pair_plan(self, pairs_global: np.ndarray, per: int) -> PairPlan:
         """The (cached) PairPlan of `pairs_global` for shards of `per` images."""

@@ -118,6 +118,14 @@ def _worker(rank, world, port, q):
             ok = ok and float(td[b + 1, 0, 0]) == 10.0 and float(td[b + 1, 0, 1]) == 1.0 and int(tc[b + 1]) == 2
         else:
             ok = ok and plan.pairs_local.tolist() == [[0, 1], [1, 2]]
+        # the same exchange into a table that already carries the slots (FeaturePipeline.shard_tables): in place
+        pipe = P.FeaturePipeline.__new__(P.FeaturePipeline)
+        tabs = pipe.shard_tables(plan, nmax, torch.device("cpu"))
+        ok = ok and tabs['desc'].shape == (b + world * plan.K, nmax, 128) and tabs['count'].shape == (b + world * plan.K,)
+        tabs['desc'][:b] = desc
+        tabs['count'][:b] = counts
+        td2, tc2 = P.exchange_for(plan, tabs['desc'], tabs['count'])
+        ok = ok and td2.data_ptr() == tabs['desc'].data_ptr() and torch.equal(td2, td) and torch.equal(tc2, tc)
         q.put((rank, bool(ok), mine.tolist()))
     finally:
         dist.destroy_process_group()
