@@ -11,7 +11,7 @@ struct SegState {                // one per (image, level)
     float    median;
     uint32_t n_cand;             // candidates appended by NMS (may exceed cap)
     uint32_t n_sel;              // selected, border-valid keypoints
-    uint32_t med_cnt;            // keys of bucket prefix[0] compacted by k_median_compact (may exceed cap)
+    uint32_t med_cnt;            // keys of bucket prefix[0] compacted by k_nms (may exceed cap)
     uint32_t min1;               // smallest key of bucket prefix[1] when it differs from prefix[0]
     uint32_t pad[7];
 };
