@@ -45,12 +45,17 @@ template <int G> struct Cfg {
     static constexpr int PPITCH = PCH * 4;               // floats per product row
     static constexpr int IPITCH = (PCH * 4 + OFF + 2 + 3) & ~3;
     static constexpr int IH = BH + 2;                    // image rows per chunk
-    static constexpr int PLANE = BH * PPITCH;            // floats per plane of a chunk
-    static constexpr int SLOT = 3 * PLANE;               // floats per ring slot
+    // Ring layout [plane][ring row][PPITCH]: the chunk in slot s is ring rows 16 s .. 16 s + 15 of every plane, so the
+    // 16 + 2R product rows a band reads are CONSECUTIVE ring rows and a consumer thread addresses them as one base
+    // register per 16-byte chunk plus an immediate.  The one exception, a band whose first chunk sits in the last slot,
+    // is removed by a shadow: rows 0 .. 2R-1 of slot 0 are also written behind the last slot.
+    static constexpr int RROWS = RING * BH + 2 * R;      // ring rows per plane, shadow included
+    static constexpr int PSTRIDE = RROWS * PPITCH;       // floats per plane
+    static constexpr int LASTV = NV - 4 * (NCH - 1);     // floats a thread needs of its last 16-byte chunk
     static constexpr int ITILE = IH * IPITCH;            // floats per staged image tile (the TMA box)
     static constexpr int ISTRIDE = (ITILE + 31) & ~31;   // stage stride: TMA destinations are 128-byte aligned
     static constexpr int EMIT = (R + 1) & ~1;            // chunk kc emits next-level rows from image row 16 kc - EMIT on (even, inside the tile)
-    static constexpr size_t ring_bytes = sizeof(float) * (size_t)SLOT * RING;
+    static constexpr size_t ring_bytes = (sizeof(float) * 3 * (size_t)PSTRIDE + 127) / 128 * 128;   // the TMA stages behind it are 128-byte aligned
     static constexpr size_t img_bytes = sizeof(float) * (size_t)ISTRIDE * ISTAGES;
     static constexpr size_t hist_bytes = sizeof(uint32_t) * SFM_HIST1_BINS;
     static constexpr size_t bar_bytes = 8 * (2 * RING + 2 * ISTAGES);
@@ -120,6 +125,7 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
         int coff[C::NCH];
 #pragma unroll
         for (int j = 0; j < C::NCH; ++j) { const int c = 2 * tx + j; coff[j] = (c ^ ((c >> 3) & 1)) * 4; }
+        const uint32_t ring_u32 = smem_u32(s_ring);
         int b0i, s0i, k0i;
         hs::decompose(g, g.n0, b0i, s0i, k0i);
         int epoch = 0;                                     // images of this CTA's range whose histogram has been flushed
@@ -152,15 +158,25 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
             const int slot0 = cs % hs::RING, slot1 = (cs + 1) % hs::RING;
             mbar_wait(bar_full(slot0), (uint32_t)((cs / hs::RING) & 1));
             mbar_wait(bar_full(slot1), (uint32_t)(((cs + 1) / hs::RING) & 1));
-            // product row jj of this thread's 4 output rows is chunk row 4*ty + jj: slot0 below BH, slot1 from BH on
-            const float* p0 = s_ring + (size_t)slot0 * C::SLOT + 4 * ty * C::PPITCH;
-            const float* p1 = s_ring + (size_t)slot1 * C::SLOT + (4 * ty - hs::BH) * C::PPITCH;
-            auto load_row = [&](int pl, int jj, float (&v)[4 * C::NCH]) {
-                const float* row = ((4 * ty + jj < hs::BH) ? p0 : p1) + pl * C::PLANE + jj * C::PPITCH;
+            // product row jj of this thread's 4 output rows is ring row 16 slot0 + 4 ty + jj of the plane (consecutive rows:
+            // see Cfg): one base register per 16-byte chunk and plane, the row as an immediate offset
+            uint32_t pbase[C::NCH];
+            auto set_plane = [&](int pl) {
+#pragma unroll
+                for (int j = 0; j < C::NCH; ++j)
+                    pbase[j] = ring_u32 + 4u * (uint32_t)(pl * C::PSTRIDE + (slot0 * hs::BH + 4 * ty) * C::PPITCH + coff[j]);
+            };
+            auto load_at = [&](uint32_t rowoff_bytes, auto imm_tag, float (&v)[4 * C::NCH]) {
+                constexpr int IMM = decltype(imm_tag)::value;
 #pragma unroll
                 for (int j = 0; j < C::NCH; ++j) {
-                    const float4 q4 = *reinterpret_cast<const float4*>(row + coff[j]);
-                    v[4 * j + 0] = q4.x; v[4 * j + 1] = q4.y; v[4 * j + 2] = q4.z; v[4 * j + 3] = q4.w;
+                    if (j == C::NCH - 1 && C::LASTV <= 2) {
+                        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2+%3];" : "=f"(v[4 * j]), "=f"(v[4 * j + 1]) : "r"(pbase[j] + rowoff_bytes), "n"(IMM));
+                        v[4 * j + 2] = 0.0f; v[4 * j + 3] = 0.0f;
+                    } else {
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+                                     : "=f"(v[4 * j]), "=f"(v[4 * j + 1]), "=f"(v[4 * j + 2]), "=f"(v[4 * j + 3]) : "r"(pbase[j] + rowoff_bytes), "n"(IMM));
+                    }
                 }
             };
             unsigned long long A[8], Bq[8];
@@ -170,12 +186,13 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
 #pragma unroll 1
             for (int pl = 0; pl < 3; ++pl) {
                 float v[4 * C::NCH];
+                set_plane(pl);
 #pragma unroll
                 for (int p = 0; p < 8; ++p) { A[p] = 0ull; Bq[p] = 0ull; }
                 auto step = [&](auto jj_tag) {
                     constexpr int jj = decltype(jj_tag)::value;
                     constexpr bool AU = (jj < G), AL = (jj >= 1 && jj <= G), BU = (jj >= 2 && jj < G + 2), BL = (jj >= 3 && jj <= G + 2);
-                    load_row(pl, jj, v);
+                    load_at(0u, std::integral_constant<int, jj * C::PPITCH * 4>{}, v);
                     harris_pair_taps<G, AU, AL>(v, gw.wp + (AU && AL ? jj : 0) * SFM_GW_PITCH, gw.w + (AU ? jj : 0) * SFM_GW_PITCH,
                                                 gw.w + (AL ? jj - 1 : 0) * SFM_GW_PITCH, A);
                     harris_pair_taps<G, BU, BL>(v, gw.wp + (BU && BL ? jj - 2 : 0) * SFM_GW_PITCH, gw.w + (BU ? jj - 2 : 0) * SFM_GW_PITCH,
@@ -187,7 +204,7 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
                 if constexpr (G >= 5) {
 #pragma unroll 1
                     for (int jj = 3; jj < G; ++jj) {
-                        load_row(pl, jj, v);
+                        load_at((uint32_t)(jj * C::PPITCH * 4), std::integral_constant<int, 0>{}, v);
                         harris_pair_taps<G, true, true>(v, gw.wp + jj * SFM_GW_PITCH, nullptr, nullptr, A);
                         harris_pair_taps<G, true, true>(v, gw.wp + (jj - 2) * SFM_GW_PITCH, nullptr, nullptr, Bq);
                     }
@@ -300,7 +317,8 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
             mbar_wait(bar_empty(c.slot), (uint32_t)(c.sph ^ 1));   // (a fresh barrier reports the phase before its first as complete)
             mbar_wait(bar_ifull(c.st), (uint32_t)c.iph);
             const float* tile = s_img + (size_t)c.st * C::ISTRIDE;
-            float* dst = s_ring + (size_t)c.slot * C::SLOT;
+            float* dst = s_ring + c.slot * hs::BH * C::PPITCH;
+            const int shadow = (c.slot == 0) ? hs::RING * hs::BH * C::PPITCH : 0;      // rows 0 .. 2R-1 of slot 0 go behind the last slot too
             const int x0 = c.s * hs::SW, y0 = kc * hs::BH;         // product row py is image row y0 - R + py
             // PCH * BH = 288 strip tasks of 4 pixels: two per thread, and a third for one warp of the group in turn
             const int ntask = C::PCH * rows;
@@ -341,8 +359,13 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
                 }
                 float* o = dst + py * C::PPITCH + (c4 ^ ((c4 >> 3) & 1)) * 4;
                 *reinterpret_cast<float4*>(o) = make_float4(xx[0], xx[1], xx[2], xx[3]);
-                *reinterpret_cast<float4*>(o + C::PLANE) = make_float4(xy[0], xy[1], xy[2], xy[3]);
-                *reinterpret_cast<float4*>(o + 2 * C::PLANE) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+                *reinterpret_cast<float4*>(o + C::PSTRIDE) = make_float4(xy[0], xy[1], xy[2], xy[3]);
+                *reinterpret_cast<float4*>(o + 2 * C::PSTRIDE) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+                if (shadow && py < 2 * C::R) {
+                    *reinterpret_cast<float4*>(o + shadow) = make_float4(xx[0], xx[1], xx[2], xx[3]);
+                    *reinterpret_cast<float4*>(o + shadow + C::PSTRIDE) = make_float4(xy[0], xy[1], xy[2], xy[3]);
+                    *reinterpret_cast<float4*>(o + shadow + 2 * C::PSTRIDE) = make_float4(yy[0], yy[1], yy[2], yy[3]);
+                }
             };
             const int t0i = pw * 32 + lane;
             if (t0i < ntask) task(t0i);
