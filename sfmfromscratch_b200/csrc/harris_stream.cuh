@@ -201,14 +201,15 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
                 step(std::integral_constant<int, 0>{});
                 step(std::integral_constant<int, 1>{});
                 step(std::integral_constant<int, 2>{});
-                if constexpr (G >= 5) {
-#pragma unroll 1
-                    for (int jj = 3; jj < G; ++jj) {
-                        load_at((uint32_t)(jj * C::PPITCH * 4), std::integral_constant<int, 0>{}, v);
-                        harris_pair_taps<G, true, true>(v, gw.wp + jj * SFM_GW_PITCH, nullptr, nullptr, A);
-                        harris_pair_taps<G, true, true>(v, gw.wp + (jj - 2) * SFM_GW_PITCH, nullptr, nullptr, Bq);
-                    }
-                }
+                // rows 3 .. G-1 (both pairs packed) peeled as well: with a compile-time row every weight pair is a
+                // uniform-register operand fetched by LDCU; left rolled, the row index lives in a vector register
+                // (ptxas does not treat it as warp-uniform inside the role branch) and the 14 weight pairs of a row
+                // arrive by indexed LDC into vector registers, ~60 clk ahead of the row's first FFMA2
+                if constexpr (G >= 5) step(std::integral_constant<int, 3>{});
+                if constexpr (G >= 5) step(std::integral_constant<int, 4>{});
+                if constexpr (G >= 7) step(std::integral_constant<int, 5>{});
+                if constexpr (G >= 7) step(std::integral_constant<int, 6>{});
+                static_assert(G <= 7, "peel rows 7 .. G-1 for larger windows");
                 if constexpr (G >= 3) {
                     step(std::integral_constant<int, G>{});
                     step(std::integral_constant<int, G + 1>{});
