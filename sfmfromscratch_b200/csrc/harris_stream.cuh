@@ -104,7 +104,9 @@ k_harris_stream(const __grid_constant__ ExtractPlan P, const __grid_constant__ G
     const long long NB = (long long)P.B * g.S * g.K;
     g.n0 = (int)(NB * blockIdx.x / gridDim.x);
     g.n1 = (int)(NB * (blockIdx.x + 1) / gridDim.x);
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    // the warp index through a shuffle: ptxas then knows it is warp-uniform and keeps the role branches, loop counters and
+    // constant-bank indices below on the uniform datapath
+    const int t = threadIdx.x, warp = __shfl_sync(0xffffffffu, t >> 5, 0), lane = t & 31;
 
     if (t == 0) {
         for (int i = 0; i < hs::RING; ++i) { mbar_init(bar_full(i), hs::NPROD); mbar_init(bar_empty(i), 2); }
