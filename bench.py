@@ -551,7 +551,9 @@ def run_ours(args):
     fp32_peak = 2.0 * 128.0 * 148 * 1.965e9 / 1e12               # TFLOP/s: 128 FMA lanes/clk/SM x 148 SMs x max SM clock
     fp32_ach = 2.0 * 147.0 * lp * per / (kh_ms_step * 1e-3) / 1e12 if kh[1] else None
     th = traffic.get("k_harris_dram_bytes_per_image")
-    roofline = {"kernel": "k_harris (fused Sobel + second moments + 7x7 window + R + next pyramid level), all 4 launches of a step",
+    roofline = {"kernel": "k_harris: k_harris_stream<7> (persistent warp-specialised: TMA tiles -> producer warps -> shared-memory ring of "
+                          "product rows -> consumer warps, 4 output rows per thread) on levels 0-2 + the tile kernel on level 3; "
+                          "fused Sobel + second moments + 7x7 window + R + histogram + next pyramid level; every launch of a step",
                 "bound": "fp32", "achieved": fp32_ach, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": (fp32_ach / fp32_peak) if fp32_ach else None,
                 "traffic": (th * per) if th else None, "traffic_source": traffic.get("_file"),
@@ -560,16 +562,17 @@ def run_ours(args):
                 "hbm": {"achieved": hbm_ach, "peak": pk["hbm"], "unit": "GB/s", "frac": (hbm_ach / pk["hbm"]) if hbm_ach else None,
                         "algorithmic_bytes_per_step": harris_bytes, "peak_source": pk["src"]},
                 "kernel_ms_per_step": kh_ms_step, "share_of_step": (kh_ms_step / prof_ms) if kh[1] else None,
-                "window_stage_alone_frac": 0.72,
+                "window_stage_alone_frac": 0.85,
                 "note": "per-kernel CUDA events on the launching stream over a repeat of the timed region; the bit-exact 3 x 49 "
                         "dependent fmaf chains per pixel make this kernel FP32-issue bound (floor = frac 1.0), which caps its HBM "
-                        "use near 0.35; window_stage_alone_frac = scripts/micro/window_rate.cu, the window stage's own ceiling"}
+                        "use near 0.35; window_stage_alone_frac = scripts/micro/window_forms.cu, the 4-row window stage alone "
+                        "at 2 warps per scheduler (0.72 for the 2-row stage of the tile kernel)"}
     # the streaming pass over R (k_nms: window maxima + median-bucket compaction): HBM-bound
     kn = kstat.get("k_nms", (0, 0.0))
     kn_ms = kn[1] / prof_steps if kn[1] else float("nan")
     nms_bytes = 4.0 * lp * per
     tn = traffic.get("k_nms_dram_bytes_per_image")
-    roofline_nms = {"kernel": "k_nms (one pass over R: window maxima + median-bucket compaction), all 4 launches of a step",
+    roofline_nms = {"kernel": "k_nms (one pass over R: window maxima + median-bucket compaction; all pyramid levels in one launch per extraction call)",
                     "bound": "hbm", "achieved": nms_bytes / (kn_ms * 1e-3) / 1e9 if kn[1] else None, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": nms_bytes / (kn_ms * 1e-3) / 1e9 / pk["hbm"] if kn[1] else None,
                     "traffic": (tn * per) if tn else None, "algorithmic_bytes_per_step": nms_bytes, "kernel_ms_per_step": kn_ms}
