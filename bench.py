@@ -543,7 +543,7 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (k_harris): FP32-pipe bound by construction (147 order-preserving
     #      FMAs per pyramid pixel), HBM beside it
     lp = level_pixels(IMG_H, IMG_W)
-    kh = kstat.get("k_harris", (0, 0.0))
+    kh = tuple(a + b for a, b in zip(kstat.get("k_harris", (0, 0.0)), kstat.get("k_harris_stream", (0, 0.0))))   # both Harris kernels
     kh_ms_step = kh[1] / prof_steps if kh[1] else float("nan")
     # 4 B read + 4 B written per pyramid pixel, + 4 B per pixel of the next (exactly halved) level it emits
     harris_bytes = (8.0 * lp + 4.0 * (lp - IMG_H * IMG_W)) * per

@@ -119,6 +119,13 @@ SFM_EXPORT int  sfm_ctx_sm_count(SfmCtx* ctx);
 /* Kernel launches issued through this context so far (bench.py's gpu_launches). */
 SFM_EXPORT unsigned long long sfm_ctx_launch_count(SfmCtx* ctx);
 
+/* Per-context tuning.  Results never depend on an option; only which kernel computes them does.
+ *   SFM_OPT_HARRIS_STREAM_MIN_BANDS  a pyramid level goes to the persistent Harris stream (k_harris_stream) when it
+ *       has at least this many 64x16 bands per SM, otherwise to the one-tile-per-CTA kernel (default 24; 0 sends
+ *       every level the stream can take -- the tests use it to run the stream on small and odd shapes). */
+#define SFM_OPT_HARRIS_STREAM_MIN_BANDS 1
+SFM_EXPORT int sfm_ctx_set_option(SfmCtx* ctx, int option, int value);
+
 /* Optional per-kernel timing: while enabled, every kernel the library launches
  * is bracketed by two CUDA events on the launching stream.  sfm_profile_collect
  * waits for the recorded events, aggregates them by kernel name into out[0..cap)

@@ -27,7 +27,7 @@ DESC_DIM = 128
 # every symbol include/sfmb200.h declares
 EXPORTS = [
     "sfm_version", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_error", "sfm_ctx_sm_count",
-    "sfm_ctx_launch_count", "sfm_profile_enable", "sfm_profile_collect",
+    "sfm_ctx_launch_count", "sfm_ctx_set_option", "sfm_profile_enable", "sfm_profile_collect",
     "sfm_extract_default_params", "sfm_extract_max_keypoints", "sfm_extract_workspace_bytes",
     "sfm_extract_batch", "sfm_extract_status", "sfm_harris_response",
     "sfm_ingest_workspace_bytes", "sfm_ingest_rgb8",
@@ -86,6 +86,7 @@ def load_library() -> C.CDLL:
         L.sfm_ctx_sm_count.argtypes = [C.c_void_p]
         L.sfm_ctx_launch_count.argtypes = [C.c_void_p]
         L.sfm_ctx_launch_count.restype = C.c_ulonglong
+        L.sfm_ctx_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.sfm_profile_enable.argtypes = [C.c_void_p, C.c_int]
         L.sfm_profile_collect.argtypes = [C.c_void_p, C.POINTER(SfmKernelStat), C.c_int]
         L.sfm_extract_default_params.argtypes = [PP]
@@ -148,6 +149,14 @@ def get_ctx(device: int = 0) -> int:
 def check(rc: int, ctx: int) -> None:
     if rc != SFM_OK:
         raise SfmError(rc, load_library().sfm_last_error(ctx).decode())
+
+
+SFM_OPT_HARRIS_STREAM_MIN_BANDS = 1
+
+
+def set_option(option: int, value: int, device: int = 0) -> None:
+    """sfm_ctx_set_option on the context of `device` (tuning only: results never depend on it)."""
+    check(load_library().sfm_ctx_set_option(get_ctx(device), option, value), get_ctx(device))
 
 
 def launch_count(device: int = 0) -> int:

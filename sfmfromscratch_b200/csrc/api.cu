@@ -80,6 +80,17 @@ int sfm_ctx_sm_count(SfmCtx* ctx) { return ctx ? ctx->sm_count : 0; }
 
 unsigned long long sfm_ctx_launch_count(SfmCtx* ctx) { return ctx ? ctx->launches.load() : 0ull; }
 
+int sfm_ctx_set_option(SfmCtx* ctx, int option, int value) {
+    if (!ctx) return SFM_ERR_BAD_ARG;
+    switch (option) {
+        case SFM_OPT_HARRIS_STREAM_MIN_BANDS:
+            if (value < 0) return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "SFM_OPT_HARRIS_STREAM_MIN_BANDS must be >= 0");
+            ctx->harris_stream_min_bands.store(value);
+            return SFM_OK;
+    }
+    return sfm_set_error(ctx, SFM_ERR_BAD_ARG, "unknown option %d", option);
+}
+
 int sfm_profile_enable(SfmCtx* ctx, int on) {
     if (!ctx) return SFM_ERR_BAD_ARG;
     std::lock_guard<std::mutex> g(ctx->mu);

@@ -18,6 +18,7 @@ struct SfmCtx {
     std::mutex mu;
     std::string err;
     void* tmap_encode = nullptr;   // cuTensorMapEncodeTiled, resolved lazily
+    std::atomic<int> harris_stream_min_bands{24};   // SFM_OPT_HARRIS_STREAM_MIN_BANDS
     // launch accounting / optional per-kernel CUDA-event timing (sfm_profile_*)
     std::atomic<unsigned long long> launches{0};
     bool prof_on = false;

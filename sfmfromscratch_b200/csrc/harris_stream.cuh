@@ -32,7 +32,6 @@ constexpr int NGROUP = 2;              // producer groups: group g computes the 
 constexpr int THREADS = 32 * (NCONS + NPROD * NGROUP);
 constexpr int REGS_PROD = 64, REGS_CONS = 192;   // setmaxnreg: 16 warps x 128 registers re-dealt between the roles
 constexpr int RING = 12;               // product chunks in flight (8 bands being read need 9)
-constexpr int MIN_BANDS_PER_CTA = 24;  // below this the fill / drain of the pipeline costs more than the tile kernel's halo
 constexpr int ISTAGES = 8;             // staged image tiles: the TMA loads run this many chunks ahead of the producers
 
 template <int G> struct Cfg {
