@@ -3,7 +3,7 @@
 #   gpurun --timeout 1500 -- 'bash scripts/profile_r02.sh r02a [bench]'
 # 1. (optional, "bench") python bench.py with default flags -> bench_n1.json
 # 2. ncu launch list (gpu__time_duration) of a 2-step bench without the CPU / all-pairs legs
-# 3. ncu --set full of every kernel of ONE 32 x 1080p extraction call (the second call of scripts/prof_extract.py)
+# 3. ncu --set full of every kernel (9 launches) of ONE 32 x 1080p extraction call (the second call of scripts/prof_extract.py)
 # 4. ncu --set full of the matcher kernels of the 66-pair 8192 x 8192 leg and of the bench-shaped 31-pair leg
 tag=${1:-r02}
 out=gpurun_out/prof_$tag
@@ -17,7 +17,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --
 echo "launch list rc=$?"
 EXT="python scripts/prof_extract.py 32 2"
 $EXT > $out/plain_extract.log 2>&1 &&
-timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:^k_' -s 12 -c 12 -o $out/extract_full -f $EXT > $out/ncu_extract.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:^k_' -s 9 -c 9 -o $out/extract_full -f $EXT > $out/ncu_extract.log 2>&1
 echo "extract full rc=$?"
 MATCH="python scripts/time_match.py --leg big --steps 2"
 $MATCH > $out/plain_match.log 2>&1 &&
