@@ -168,13 +168,17 @@ def exchange_for(plan: PairPlan, desc: torch.Tensor, counts: torch.Tensor, group
     own_d, own_c = desc[:plan.per], counts[:plan.per]           # (the table may carry the exchange slots behind them)
     blk = int(np.prod(desc.shape[1:]))                         # floats per descriptor block
     # ONE collective: the K blocks and their K counts travel in one packed float32 buffer (the counts as raw int32
-    # bits behind the blocks); two small all-gathers cost their launch latency twice (~0.05 ms per step at N = 8)
+    # bits behind the blocks); two small all-gathers cost their launch latency twice (~0.05 ms per step at N = 8).
+    # The two buffers live with the plan (allocated and zeroed once per device and block shape).
     kpad = (K + 3) // 4 * 4
-    send = torch.zeros((K * blk + kpad,), dtype=torch.float32, device=desc.device)
+    key = ("xbuf", str(desc.device), blk, world)
+    if key not in plan._dev:
+        plan._dev[key] = (torch.zeros((K * blk + kpad,), dtype=torch.float32, device=desc.device),
+                          torch.empty((world, K * blk + kpad), dtype=torch.float32, device=desc.device))
+    send, got = plan._dev[key]
     if n_own:
-        send[:n_own * blk].view(n_own, *desc.shape[1:]).copy_(own_d.index_select(0, idx))
-        send[K * blk:K * blk + n_own].view(torch.int32).copy_(own_c.index_select(0, idx).to(torch.int32))
-    got = torch.empty((world, K * blk + kpad), dtype=torch.float32, device=desc.device)
+        torch.index_select(own_d.reshape(plan.per, blk), 0, idx, out=send[:n_own * blk].view(n_own, blk))
+        send[K * blk:K * blk + n_own].view(torch.int32).copy_(own_c.index_select(0, idx))
     try:
         dist.all_gather_into_tensor(got, send, group=group)
     except (RuntimeError, NotImplementedError):                # backends without the fused form
