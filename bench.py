@@ -477,12 +477,22 @@ def run_ours(args):
     shard = pipe.shard_tables(plan, cap, dev)
     bounds = [(b0, min(b0 + batch, per)) for b0 in range(0, per, batch)]
 
+    last = {}
+
     def step():
-        # no host wait inside a step: the candidate-overflow flags accumulate on the device and are read
-        # once after the timed region (pipe.overflow_since_last_check)
-        for b0, b1 in bounds:
-            pipe.extract(images[b0:b1], deferred_check=True, out={k: v[b0:b1] for k, v in shard.items()})
-        return pipe.match_plan(plan, shard['desc'], shard['count'], cap=cap)
+        # FeaturePipeline.stream_resident: extraction in calls of `batch` frames on the current stream, exchange +
+        # matching on a second stream (under the next step's extraction), two sets of result tables used alternately.
+        # No host wait inside a step: the candidate-overflow flags accumulate on the device and are read once after
+        # the timed region (pipe.overflow_since_last_check).  The timed region ends with a device-wide synchronize, so
+        # every step's matching is inside it.
+        if args.serial_step:
+            for b0, b1 in bounds:
+                pipe.extract(images[b0:b1], deferred_check=True, out={k: v[b0:b1] for k, v in shard.items()})
+            last['tabs'] = shard
+            return pipe.match_plan(plan, shard['desc'], shard['count'], cap=cap)
+        tabs, m, ev = pipe.stream_resident(images, plan, batch=batch, cap=cap)
+        last['tabs'], last['ev'] = tabs, ev
+        return m
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -492,6 +502,7 @@ def run_ours(args):
         a.record()
         for _ in range(steps):
             fn()
+        pipe.join_resident()          # the closing event is recorded behind the matcher stream of stream_resident as well
         b.record()
         barrier()
         ms = torch.tensor([a.elapsed_time(b)], device=dev)
@@ -515,8 +526,9 @@ def run_ours(args):
     pixels_per_step = n_job * IMG_H * IMG_W
     value = pixels_per_step / (ms_per_step * 1e-3) / 1e6
     mcount = step()
+    torch.cuda.synchronize()
     matches_per_pair = float(mcount[2].float().mean().item()) if mcount is not None else None
-    kp_per_image = float(shard['count'][:per].float().mean().item())
+    kp_per_image = float(last['tabs']['count'][:per].float().mean().item())
 
     # ---- the same step for >= 2 s: what the clocks do under seconds of load
     n_sust = max(args.steps, int(math.ceil(2200.0 / ms_per_step)))
@@ -851,6 +863,7 @@ def main():
     ap.add_argument("--no-all-pairs", action="store_true", help="skip the configs[4] leg")
     ap.add_argument("--no-geometry", action="store_true", help="skip the RANSAC / association leg (SURVEY 8f rows 2-3)")
     ap.add_argument("--port-only", action="store_true", help="--impl reference: time the oracle port only")
+    ap.add_argument("--serial-step", action="store_true", help="matching behind the extraction on one stream (no overlap across steps)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

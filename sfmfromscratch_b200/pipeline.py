@@ -302,6 +302,55 @@ class FeaturePipeline:
                 pairs = torch.from_numpy(inv.reshape(-1, 2).astype(np.int32)).to(desc_all.device, non_blocking=True)
         return match_batch_device(desc_all, counts_all, pairs, self.ratio_threshold, cap=cap)
 
+    def stream_resident(self, images: torch.Tensor, plan: PairPlan, batch: int = 32, cap: Optional[int] = None):
+        """One job over a RESIDENT shard, for a sequence of jobs: extraction of `images` ([per, H, W] on the device) in
+        calls of `batch` frames on the current stream, then the exchange `plan` needs and the matching of this rank's
+        pairs on a second stream -- so job k's matcher (latency-bound gathers that leave most of the SMs' issue slots
+        idle) runs under job k+1's extraction instead of behind it.  Two sets of result tables are used alternately; a
+        set is reused only after the matching that read it has finished (events, no host wait).  Candidate-overflow
+        flags accumulate as in `extract(deferred_check=True)`.  Returns (tables, match result or None, completion
+        event): the tables and the match tensors are valid once the event has completed, and until the job after next."""
+        dev = images.device
+        main = torch.cuda.current_stream()
+        per = images.shape[0]
+        cap = cap or self.max_keypoints()
+        key = (id(plan), per, cap, dev.index)
+        if getattr(self, '_res_key', None) != key:
+            if getattr(self, '_res_sets', None):
+                for st in self._res_sets:
+                    if st['free'] is not None:
+                        st['free'].synchronize()
+            self._s_match = getattr(self, '_s_match', None) or torch.cuda.Stream()
+            self._res_sets = [dict(self.shard_tables(plan, cap, dev), free=None) for _ in range(2)]
+            self._res_key, self._res_i = key, 0
+        st = self._res_sets[self._res_i]
+        self._res_i ^= 1
+        if st['free'] is not None:
+            main.wait_event(st['free'])                         # the matching that last read this set is done
+        tabs = {k: st[k] for k in ('x', 'y', 'count', 'desc')}
+        for b0 in range(0, per, batch):
+            b1 = min(b0 + batch, per)
+            self.extract(images[b0:b1], deferred_check=True, out={k: v[b0:b1] for k, v in tabs.items()})
+        ready = torch.cuda.Event()
+        ready.record(main)
+        self._s_match.wait_event(ready)
+        with torch.cuda.stream(self._s_match):
+            m = self.match_plan(plan, tabs['desc'], tabs['count'], cap=cap)
+            st['free'] = torch.cuda.Event()
+            st['free'].record(self._s_match)
+        return tabs, m, st['free']
+
+    def join_resident(self) -> None:
+        """The current stream waits for the matching `stream_resident` has put on its second stream (no host wait)."""
+        if getattr(self, '_s_match', None) is not None:
+            torch.cuda.current_stream().wait_stream(self._s_match)
+
+    def max_keypoints(self) -> int:
+        """Rows of the result tables: sfm_extract_max_keypoints of this pipeline's parameters."""
+        import ctypes as C
+        from . import _native as N
+        return int(N.load_library().sfm_extract_max_keypoints(C.byref(self.params)))
+
     def run_host(self, host_images: torch.Tensor, pairs_global: np.ndarray, host_out: dict, chunk: int = 8,
                  _params=None):
         """The hot path end to end from HOST buffers: `host_images` is a pinned

@@ -134,3 +134,38 @@ def test_matcher_batch_above_grid_limit_and_bad_pair_ids():
     m2, c2, cnt2 = match_batch_device(torch.from_numpy(desc).to(dev), torch.from_numpy(counts).to(dev),
                                       torch.from_numpy(pairs[30000:]).to(dev), 0.8, cap=nmax)
     assert np.array_equal(cnt[30000:], cnt2.cpu().numpy())
+
+
+def test_stream_resident_equals_serial_step(bench_batch):
+    """bench.py's step (FeaturePipeline.stream_resident: matching on a second stream under the next job's extraction,
+    two table sets used alternately) returns, job after job, exactly what extraction followed by match_plan returns."""
+    import torch
+    from sfmfromscratch_b200 import pipeline as PL
+    frames, host, plan, (mm, mc, mn) = bench_batch
+    dev = torch.device("cuda", 0)
+    images = torch.from_numpy(frames).to(dev)
+    pipe = PL.FeaturePipeline({}, 0.8)
+    plan2 = pipe.pair_plan(PL.consecutive_pairs(32), 32)
+    jobs = []
+    for _ in range(4):                                   # both table sets twice, no host wait in between
+        tabs, m, ev = pipe.stream_resident(images, plan2, batch=8, cap=2500)
+        jobs.append((tabs, m, ev))
+    pipe.join_resident()
+    torch.cuda.synchronize()
+    assert not pipe.overflow_since_last_check()
+    assert jobs[0][0]['desc'].data_ptr() == jobs[2][0]['desc'].data_ptr() != jobs[1][0]['desc'].data_ptr()
+    for tabs, m, ev in jobs[2:]:                         # (the first two jobs' tables have been overwritten by these)
+        assert ev.query()
+        for k in ('x', 'y', 'count', 'desc'):
+            got = tabs[k].cpu().numpy()
+            if k == 'count':
+                assert np.array_equal(got[:32], host[k])
+            else:
+                for b in range(32):
+                    n = int(host['count'][b])
+                    assert np.array_equal(got[b, :n], host[k][b, :n])
+        for a, b in zip(m, (mm, mc, mn)):
+            a = a.cpu().numpy()
+            for k in range(31):
+                n = int(mn[k])
+                assert np.array_equal(a[k][:n] if a.ndim > 1 else a[k], b[k][:n] if b.ndim > 1 else b[k])
