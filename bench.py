@@ -486,13 +486,18 @@ def run_ours(args):
         # the timed region (pipe.overflow_since_last_check).  The timed region ends with a device-wide synchronize, so
         # every step's matching is inside it.
         if args.serial_step:
-            for b0, b1 in bounds:
-                pipe.extract(images[b0:b1], deferred_check=True, out={k: v[b0:b1] for k, v in shard.items()})
-            last['tabs'] = shard
-            return pipe.match_plan(plan, shard['desc'], shard['count'], cap=cap)
+            return step_serial()
         tabs, m, ev = pipe.stream_resident(images, plan, batch=batch, cap=cap)
         last['tabs'], last['ev'] = tabs, ev
         return m
+
+    def step_serial():
+        # the same work on ONE stream (matching behind the extraction): what the per-kernel pass times, because a
+        # kernel's event interval means nothing while another stream's kernels share the device
+        for b0, b1 in bounds:
+            pipe.extract(images[b0:b1], deferred_check=True, out={k: v[b0:b1] for k, v in shard.items()})
+        last['tabs'] = shard
+        return pipe.match_plan(plan, shard['desc'], shard['count'], cap=cap)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -540,9 +545,11 @@ def run_ours(args):
 
     # ---- the same K steps again with the library's per-kernel CUDA events switched on (two event
     #      records per launch cost a few per cent, so `value` comes from the clean region above)
-    N.profile_enable(True, local)
+    #      -- on one stream (step_serial), so that every kernel's event interval is its own
     prof_steps = min(args.steps, 50)
-    prof_ms = timed(step, prof_steps, 0) / prof_steps
+    serial_ms = timed(step_serial, prof_steps, 2) / prof_steps
+    N.profile_enable(True, local)
+    prof_ms = timed(step_serial, prof_steps, 0) / prof_steps
     kstat = N.profile_collect(local)
     N.profile_enable(False, local)
     kernels = {k: {"launches_per_step": v[0] / prof_steps, "ms_per_step": v[1] / prof_steps} for k, v in sorted(kstat.items())}
@@ -838,12 +845,15 @@ def run_ours(args):
                                        "(sfmfromscratch_b200.synth.frame_sequence)",
                            "l2": f"inputs larger than L2 ({per * IMG_H * IMG_W * 4 / 1e6:.0f} MB of distinct frames per GPU and step, "
                                  f"{batch * lp * 4 / 1e6:.0f} MB of R planes per batch)",
+                           "step": ("FeaturePipeline.stream_resident: extraction on the current stream, exchange + matching of the same job on a "
+                                    "second stream under the next job's extraction (ms_per_step_serial = everything on one stream; the "
+                                    "per-kernel times come from that serial form)") if not args.serial_step else "extraction, exchange, matching on one stream",
                            "parallelism": f"image shards x{world}, all-gather (NCCL) of the {plan.K} descriptor block(s) per rank that "
                                           f"another shard's pairs need (policy {plan.policy}), pair shards"},
                 "roofline": roofline, "roofline_nms": roofline_nms, "extraction": extraction,
                 "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
                 "clocks": clocks, "sustained": sustained, "exchange_ms": exchange_ms,
-                "ms_per_step_profiled": prof_ms, "kernels": kernels, "all_pairs": ap_leg, "match": match,
+                "ms_per_step_serial": serial_ms, "ms_per_step_profiled": prof_ms, "kernels": kernels, "all_pairs": ap_leg, "match": match,
                 "single_image": single, "config0_two_view": config0, "config2_4k_pair": cfg2, "geometry": geom}
         print(json.dumps(line), flush=True)
     if world > 1:

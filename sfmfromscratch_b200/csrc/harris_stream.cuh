@@ -12,10 +12,12 @@
 // So the phases are decoupled instead of interleaved by occupancy.  One persistent CTA per SM, 16 warps:
 //   warps 8-15  CONSUMERS: the window stage only, 4 rows x 8 px per thread (a warp = one 64 x 16 band), product rows
 //               read from a shared-memory ring, R stored from registers, first radix-select histogram;
-//   warps 0-7   PRODUCERS (two groups of four, alternating chunks): Sobel + the three products (NaiveSIFT.py:61-64) of one 16-row chunk at a time, from a
-//               TMA-staged image tile (cp.async.bulk.tensor, zero fill outside the image == BORDER_CONSTANT, issued
-//               ISTAGES - 2 chunks ahead by the producer warps in turn) into the ring; they also emit the strip's part
-//               of pyramid level l+1 (the exact 2x2 mean) from the tile they hold.
+//   warps 0-7   PRODUCERS (two groups of four, alternating chunks): Sobel + the three products (NaiveSIFT.py:61-64)
+//               of one 16-row chunk at a time, from a TMA-staged image tile (cp.async.bulk.tensor, zero fill outside
+//               the image == BORDER_CONSTANT, issued ISTAGES - NGROUP chunks ahead by the group's warps in turn) into
+//               the ring; they also emit the strip's part of pyramid level l+1 (the exact 2x2 mean) from that tile.
+// Registers are re-dealt between the roles with setmaxnreg; the warp index is taken through __shfl_sync so that ptxas
+// knows it is warp-uniform (role-local loop counters and constant-bank indices then stay on the uniform datapath).
 // The image is cut into vertical strips of 64 columns and each strip into bands of 16 rows; the launch's bands
 // (image-major, strip, band) are dealt to the CTAs as equal contiguous ranges.  Inside a range, consecutive bands of
 // one strip form a run: band k needs product rows [16k-R, 16k+16+R) = chunk k plus the first 2R rows of chunk k+1,
@@ -32,7 +34,7 @@ constexpr int NGROUP = 2;              // producer groups: group g computes the 
 constexpr int THREADS = 32 * (NCONS + NPROD * NGROUP);
 constexpr int REGS_PROD = 64, REGS_CONS = 192;   // setmaxnreg: 16 warps x 128 registers re-dealt between the roles
 constexpr int RING = 12;               // product chunks in flight (8 bands being read need 9)
-constexpr int ISTAGES = 8;             // staged image tiles: the TMA loads run this many chunks ahead of the producers
+constexpr int ISTAGES = 8;             // staged image tiles (each producer group cycles through ISTAGES / NGROUP of them)
 
 template <int G> struct Cfg {
     static constexpr int R = G / 2;
