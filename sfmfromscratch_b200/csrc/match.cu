@@ -154,8 +154,9 @@ constexpr int RC_SQ_STRIDE = SFM_DESC_DIM + 8;   // staging row of squares: 544 
 // (d1 = 0 makes k_match_emit skip the row).  Surviving rows are compacted so that phase 2 runs
 // with full teams.
 // Phase 2 (8 lanes per row): as described above.
-template <int NV>
+template <int NV, int GRP>
 __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant__ MatchPlan P, int rows_per_cta) {
+    using G = MtG<GRP>;
     extern __shared__ __align__(16) unsigned char rc_smem[];
     float (*s_sq)[MT_SUB][RC_SQ_STRIDE] = reinterpret_cast<float (*)[MT_SUB][RC_SQ_STRIDE]>(rc_smem);
     __shared__ double s_ebase[RC_ROWS], s_na[RC_ROWS];
@@ -273,8 +274,8 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
         auto group_col = [&](uint32_t wc) -> int {
             const int list = (int)(wc >> MT_IDX_BITS);
             const int split = list >> 1, half = list & 1;
-            const int tile = split * P.tiles_per_split + (int)((wc & MT_IDX_MASK) >> MT_GROUP_BITS);
-            return tile * MT_COLS + half * (MT_COLS / 2) + (int)(wc & (MT_GROUPS_PER_HALF - 1)) * MT_GROUP;
+            const int tile = split * P.tiles_per_split + (int)((wc & MT_IDX_MASK) >> G::GROUP_BITS);
+            return tile * MT_COLS + half * (MT_COLS / 2) + (int)(wc & (G::GROUPS_PER_HALF - 1)) * G::GROUP;
         };
         // 4 columns as full lines: v[4 cc + i] = elements 32 i + 4 j .. + 3 of column col0 + cc
         auto group_load = [&](int col0, float4 (&v)[16]) {
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(256, 2) k_match_recheck(const __grid_constant_
         // NG candidate groups, MT_SUB columns at a time; the next sub-group's loads are issued once the
         // current one's registers are free and fly under its summation
         auto visit = [&](const int (&cols)[2], auto ng_tag) {
-            constexpr int SPG = MT_GROUP / MT_SUB;
+            constexpr int SPG = G::GROUP / MT_SUB;
             constexpr int NS = decltype(ng_tag)::value * SPG;
             float4 v[16];
             group_load(cols[0], v);
@@ -411,8 +412,13 @@ static int launch_match_recheck(SfmCtx* ctx, cudaStream_t s, const MatchPlan& P)
     constexpr int smem = RC_TEAMS * MT_SUB * RC_SQ_STRIDE * (int)sizeof(float);
 #define RC_GO(NV)                                                                                          \
     do {                                                                                                   \
-        SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_recheck<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
-        SFM_LAUNCH(ctx, s, "k_match_recheck", k_match_recheck<NV><<<grid, 256, smem, s>>>(P, rows));       \
+        if (P.group == 4) {                                                                                \
+            SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_recheck<NV, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            SFM_LAUNCH(ctx, s, "k_match_recheck", k_match_recheck<NV, 4><<<grid, 256, smem, s>>>(P, rows)); \
+        } else {                                                                                           \
+            SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_recheck<NV, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
+            SFM_LAUNCH(ctx, s, "k_match_recheck", k_match_recheck<NV, 8><<<grid, 256, smem, s>>>(P, rows)); \
+        }                                                                                                  \
     } while (0)
     if (nv <= 1) RC_GO(1);
     else if (nv <= 2) RC_GO(2);
@@ -847,7 +853,8 @@ __global__ void __launch_bounds__(256) k_match_sort_big(const __grid_constant__ 
 static int choose_splits(int n_pairs, int nmax_pad) {
     const int n_tiles = nmax_pad / MT_COLS;
     const int rowblocks = nmax_pad / MT_ROWS;
-    const int min_s = (n_tiles + MT_MAX_TILES - 1) / MT_MAX_TILES;
+    const int max_tiles = mt_max_tiles(mt_group_for(nmax_pad));
+    const int min_s = (n_tiles + max_tiles - 1) / max_tiles;
     const long long base = (long long)n_pairs * rowblocks;
     // B200: 148 SMs.  A constant on purpose -- the split count sizes the workspace, and
     // sfm_match_workspace_bytes has no context to ask (sfm_ctx_create accepts sm_100 devices only)
@@ -878,6 +885,7 @@ static void match_layout(int n_sets, int nmax, int n_pairs, MatchPlan& P, MatchW
     P.n_sets = n_sets; P.nmax = nmax; P.n_pairs = n_pairs;
     P.nmax_pad = (int)align_up((size_t)std::max(nmax, 1), MT_ROWS);
     P.n_tiles = P.nmax_pad / MT_COLS;
+    P.group = mt_group_for(P.nmax_pad);
     P.n_splits = choose_splits(n_pairs, P.nmax_pad);
     P.tiles_per_split = (P.n_tiles + P.n_splits - 1) / P.n_splits;
     P.n_lists = 2 * P.n_splits;

@@ -12,7 +12,7 @@
 // as the pipeline: the epilogue drains half 0 while the tensor pipe works on
 // half 1 of the same column tile, and vice versa.
 // The epilogue warps turn each accumulator straight into the ranking key
-// |b|^2 - 2 a.b  and keep, per query row, the 4 smallest groups of MT_GROUP
+// |b|^2 - 2 a.b  and keep, per query row, the 4 smallest groups of GRP (4 or 8)
 // columns.  The distance matrix never leaves TMEM / registers; the only global
 // output is 16 bytes per (row, list).
 //
@@ -148,8 +148,10 @@ __device__ __forceinline__ void top4_insert(float (&m)[4], float k) {
     m[1] = n1; m[2] = n2; m[3] = n3;
 }
 
+template <int GRP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_match_tc(const __grid_constant__ MatchPlan P, const __grid_constant__ CUtensorMap tmap, int n_units) {
+    using G = MtG<GRP>;
     extern __shared__ unsigned char smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;      // SWIZZLE_128B tiles need 1024 B alignment
     unsigned char* sgen = smem_raw + (sbase - smem_u32(smem_raw));
@@ -279,23 +281,23 @@ k_match_tc(const __grid_constant__ MatchPlan P, const __grid_constant__ CUtensor
 #pragma unroll
                     for (int i = 0; i < 4; ++i) pre[i] = nbrow[(t + 1) * MT_COLS + 32 * i];
                 }
-                const uint32_t tile_bits = (uint32_t)(t - u.t0) << MT_GROUP_BITS;
-                // 32 accumulator columns -> 32 / MT_GROUP candidate groups of row (q, lane) of half rt
+                const uint32_t tile_bits = (uint32_t)(t - u.t0) << G::GROUP_BITS;
+                // 32 accumulator columns -> 32 / G::GROUP candidate groups of row (q, lane) of half rt
                 auto process = [&](const uint32_t (&v)[32], int rt, int c) {
 #pragma unroll
-                    for (int g = 0; g < 32 / MT_GROUP; ++g) {
+                    for (int g = 0; g < 32 / G::GROUP; ++g) {
                         float gm = 3.0e38f;
 #pragma unroll
-                        for (int e = 0; e < MT_GROUP; e += 4) {
-                            const float4 nb4 = *reinterpret_cast<const float4*>(nbs + c * 32 + g * MT_GROUP + e);
-                            const float k0 = __fmaf_rn(__uint_as_float(v[MT_GROUP * g + e + 0]), -2.0f, nb4.x);
-                            const float k1 = __fmaf_rn(__uint_as_float(v[MT_GROUP * g + e + 1]), -2.0f, nb4.y);
-                            const float k2 = __fmaf_rn(__uint_as_float(v[MT_GROUP * g + e + 2]), -2.0f, nb4.z);
-                            const float k3 = __fmaf_rn(__uint_as_float(v[MT_GROUP * g + e + 3]), -2.0f, nb4.w);
+                        for (int e = 0; e < G::GROUP; e += 4) {
+                            const float4 nb4 = *reinterpret_cast<const float4*>(nbs + c * 32 + g * G::GROUP + e);
+                            const float k0 = __fmaf_rn(__uint_as_float(v[G::GROUP * g + e + 0]), -2.0f, nb4.x);
+                            const float k1 = __fmaf_rn(__uint_as_float(v[G::GROUP * g + e + 1]), -2.0f, nb4.y);
+                            const float k2 = __fmaf_rn(__uint_as_float(v[G::GROUP * g + e + 2]), -2.0f, nb4.z);
+                            const float k3 = __fmaf_rn(__uint_as_float(v[G::GROUP * g + e + 3]), -2.0f, nb4.w);
                             const float g4 = fminf(fminf(k0, k1), fminf(k2, k3));
                             gm = (e == 0) ? g4 : fminf(gm, g4);
                         }
-                        const uint32_t pk = (__float_as_uint(gm) & ~MT_IDX_MASK) | tile_bits | (uint32_t)(c * (32 / MT_GROUP) + g);
+                        const uint32_t pk = (__float_as_uint(gm) & ~MT_IDX_MASK) | tile_bits | (uint32_t)(c * (32 / G::GROUP) + g);
                         top4_insert(m[rt], __uint_as_float(pk));
                     }
                 };
@@ -375,8 +377,13 @@ int launch_match_tc(SfmCtx* ctx, cudaStream_t st, const MatchPlan& P) {
                                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return sfm_set_error(ctx, SFM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     const int n_units = P.pn * (P.nmax_pad / MT_ROWS) * P.n_splits;
-    SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
     const int grid = n_units < ctx->sm_count ? n_units : ctx->sm_count;
-    SFM_LAUNCH(ctx, st, "k_match_tc", k_match_tc<<<grid, TC_THREADS, TC_SMEM, st>>>(P, tmap, n_units));
+    if (P.group == 4) {
+        SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_tc<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        SFM_LAUNCH(ctx, st, "k_match_tc", k_match_tc<4><<<grid, TC_THREADS, TC_SMEM, st>>>(P, tmap, n_units));
+    } else {
+        SFM_CUDA_CHECK(ctx, cudaFuncSetAttribute(k_match_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM));
+        SFM_LAUNCH(ctx, st, "k_match_tc", k_match_tc<8><<<grid, TC_THREADS, TC_SMEM, st>>>(P, tmap, n_units));
+    }
     return SFM_OK;
 }
