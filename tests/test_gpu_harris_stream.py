@@ -73,3 +73,11 @@ def test_stream_and_tile_kernels_agree_bitwise(stream_everywhere):
     assert "k_harris_stream" in sa and "k_harris_stream" not in sb
     for ra, rb in zip(a, b):
         assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]) and np.array_equal(ra[2], rb[2])
+
+
+def test_set_option_rejects_what_it_does_not_know(stream_everywhere):
+    N = stream_everywhere
+    with pytest.raises(N.SfmError):
+        N.set_option(999, 1)
+    with pytest.raises(N.SfmError):
+        N.set_option(N.SFM_OPT_HARRIS_STREAM_MIN_BANDS, -1)
