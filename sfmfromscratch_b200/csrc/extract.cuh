@@ -52,6 +52,9 @@ struct ExtractPlan {
     int* flags;                  // [0]: candidate overflow
     double e9[9];                // np.linspace(-pi, pi, 9)
     double e37[37];              // np.linspace(-pi, pi, 37)
+    float ef37[37];              // smallest float32 >= e37[i]: (double)o >= e37[i]  <=>  o >= ef37[i] for a float32 o
+    float ef37_top;              // largest float32 <= e37[36]
+    double atan_poly[19];        // coefficients of atan2_f32 (constant-bank operands of its DFMAs)
 };
 
 // Window weights, one row of the G x G kernel per 16 floats (64-byte aligned rows: the rolled
