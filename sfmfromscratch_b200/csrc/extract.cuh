@@ -54,6 +54,10 @@ struct ExtractPlan {
     double e37[37];              // np.linspace(-pi, pi, 37)
     float ef37[37];              // smallest float32 >= e37[i]: (double)o >= e37[i]  <=>  o >= ef37[i] for a float32 o
     float ef37_top;              // largest float32 <= e37[36]
+    // slot_thr[b][k], k < 8: the smallest float32 o with (double)o - dom_b >= e9[k] (dom_b = centre of orientation bin b;
+    // row 36: no rotation, dom = 0); [b][8]: the largest float32 o with (double)o - dom_b <= e9[8].  The 8-bin
+    // histogram's float64 edge tests on a float32 orientation, decided in float32.
+    float slot_thr[37][10];
     double atan_poly[19];        // coefficients of atan2_f32 (constant-bank operands of its DFMAs)
 };
 
