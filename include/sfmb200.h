@@ -145,6 +145,20 @@ SFM_EXPORT void sfm_extract_default_params(SfmExtractParams* p);
  * (levels * per-level k): the row capacity the output arrays need. */
 SFM_EXPORT int  sfm_extract_max_keypoints(const SfmExtractParams* p);
 
+/*
+ * HOST function (no device work): the float32 decision tables of the descriptor stage, for inspection and tests.
+ * The reference bins float32 orientations against float64 edges (ScaleRotInvSIFT.py:66-87: np.histogram with
+ * np.linspace(-pi, pi, 37) and, after the float64 shift by the dominant bin's centre, np.linspace(-pi, pi, 9));
+ * the kernel decides the same tests on float32 thresholds:
+ *   ef37[i], i < 37:      the smallest float32 o with (double)o >= linspace37[i];  ef37[37]: the largest float32 o
+ *                         with (double)o <= linspace37[36]
+ *   slot_thr[b][k], k < 8: the smallest float32 o with (double)o - centre_b >= linspace9[k]  (b < 36: dominant
+ *                         bin b; b = 36: no rotation, centre 0);  [b][8]: the largest float32 o with
+ *                         (double)o - centre_b <= linspace9[8];  [b][9]: +inf (padding)
+ * ef37 has 38 floats, slot_thr 37 * 10.
+ */
+SFM_EXPORT int sfm_describe_tables(float* ef37, float* slot_thr);
+
 /* Workspace size in bytes for a batch of B images of H x W. */
 SFM_EXPORT size_t sfm_extract_workspace_bytes(int B, int H, int W, const SfmExtractParams* p);
 

@@ -29,7 +29,7 @@ EXPORTS = [
     "sfm_version", "sfm_ctx_create", "sfm_ctx_destroy", "sfm_last_error", "sfm_ctx_sm_count",
     "sfm_ctx_launch_count", "sfm_ctx_set_option", "sfm_profile_enable", "sfm_profile_collect",
     "sfm_extract_default_params", "sfm_extract_max_keypoints", "sfm_extract_workspace_bytes",
-    "sfm_extract_batch", "sfm_extract_status", "sfm_harris_response",
+    "sfm_extract_batch", "sfm_extract_status", "sfm_harris_response", "sfm_describe_tables",
     "sfm_ingest_workspace_bytes", "sfm_ingest_rgb8",
     "sfm_match_workspace_bytes", "sfm_match_prepared_bytes", "sfm_match_ratio", "sfm_match_ratio_batch",
     "sfm_matches_to_coords", "sfm_ransac_sample_indices", "sfm_ransac_workspace_bytes", "sfm_find_inliers",
@@ -111,6 +111,7 @@ def load_library() -> C.CDLL:
                                             C.c_int, vp, C.c_size_t, i32p, fp, i32p, i32p, C.c_int]
         L.sfm_matches_to_coords.argtypes = [vp, vp, i32p, i32p, i32p, i32p, i32p, i32p, C.c_int, vp, vp, i32p]
         L.sfm_ransac_sample_indices.argtypes = [C.c_uint32, C.c_int, C.c_int, vp]
+        L.sfm_describe_tables.argtypes = [vp, vp]
         L.sfm_ransac_workspace_bytes.argtypes = [C.c_int]
         L.sfm_ransac_workspace_bytes.restype = C.c_size_t
         L.sfm_find_inliers.argtypes = [vp, vp, vp, vp, C.c_int, i32p, C.c_int, C.c_double, vp, C.c_size_t, i32p, i32p, vp]
@@ -157,6 +158,17 @@ SFM_OPT_HARRIS_STREAM_MIN_BANDS = 1
 def set_option(option: int, value: int, device: int = 0) -> None:
     """sfm_ctx_set_option on the context of `device` (tuning only: results never depend on it)."""
     check(load_library().sfm_ctx_set_option(get_ctx(device), option, value), get_ctx(device))
+
+
+def describe_tables():
+    """(ef37 [38], slot_thr [37, 10]) float32: the descriptor stage's decision thresholds (host function, no GPU)."""
+    import numpy as np
+    ef37 = np.zeros(38, np.float32)
+    slot = np.zeros((37, 10), np.float32)
+    rc = load_library().sfm_describe_tables(ef37.ctypes.data, slot.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"sfm_describe_tables failed with {rc}")
+    return ef37, slot
 
 
 def launch_count(device: int = 0) -> int:
